@@ -1,0 +1,75 @@
+"""ctypes binding of libabcgpt.so (C ABI declared in include/abcgpt.h).
+
+The product path has no CPU or PyTorch fallback: if the shared object is missing (or a call fails) the ops
+raise.  `lib()` loads lazily so that host-only code (config, checkpoint I/O, CPU tests of the host logic) can
+import the package on a machine without the built extension.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libabcgpt.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "abcgpt.h")
+
+EPI_BF16, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_F32_RED, EPI_F32 = range(6)
+
+_P = c_void_p
+_SIGNATURES = {
+    "abcgpt_version": (c_int, []),
+    "abcgpt_last_error": (c_char_p, []),
+    "abcgpt_gemm_bf16": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P,
+                                 c_int64, _P, c_int64, _P, c_int, c_int, _P]),
+    "abcgpt_embed_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "abcgpt_embed_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "abcgpt_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "abcgpt_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "abcgpt_attn_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "abcgpt_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "abcgpt_ce_fwd": (c_int, [_P, c_int64, _P, _P, c_int, c_int, _P]),
+    "abcgpt_ce_finalize": (c_int, [_P, _P, c_int, _P, _P, _P]),
+    "abcgpt_ce_bwd": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, _P]),
+    "abcgpt_sumsq": (c_int, [_P, c_int64, _P, _P]),
+    "abcgpt_adamw": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, _P,
+                             c_float, _P]),
+    "abcgpt_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "abcgpt_argmax": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P]),
+}
+
+_lib = None
+
+
+class AbcgptError(RuntimeError):
+    pass
+
+
+def declared_symbols() -> list[str]:
+    """Every function include/abcgpt.h declares (used by the CPU-side ABI test)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\b(abcgpt_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AbcgptError(
+                f"{LIB_PATH} is missing: build it with `python -m ai_music_generation_b200.build` "
+                "(there is no CPU/PyTorch fallback for the sm_100a kernels)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().abcgpt_last_error()
+        raise AbcgptError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

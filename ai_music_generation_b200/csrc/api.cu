@@ -1,0 +1,75 @@
+// extern "C" surface of libabcgpt (declared in include/abcgpt.h).  Plain pointers and sizes only; no torch
+// types, no exceptions across the boundary.
+#include "common.h"
+#include "kernels.h"
+
+using namespace abcgpt;
+
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int abcgpt_version(void) { return ABCGPT_VERSION; }
+const char* abcgpt_last_error(void) { return last_error_buf(); }
+
+int abcgpt_gemm_bf16(const void* a, int a_mn_major, int64_t lda, const void* b, int b_mn_major, int64_t ldb, int M,
+                     int N, int K, int epilogue, void* c, int64_t ldc, void* c2, int64_t ldc2, const void* aux,
+                     int64_t ldaux, const float* bias, int tile_n, int splits, void* stream) {
+  return gemm_bf16(a, a_mn_major, lda, b, b_mn_major, ldb, M, N, K, epilogue, c, ldc, c2, ldc2, aux, ldaux, bias,
+                   tile_n, splits, S(stream));
+}
+
+int abcgpt_embed_fwd(const int64_t* idx, const float* wte, const float* wpe, float* x, int M, int T, int C, int V,
+                     void* stream) {
+  return embed_fwd(idx, wte, wpe, x, M, T, C, V, S(stream));
+}
+int abcgpt_embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int M, int T, int C, int V,
+                     void* stream) {
+  return embed_bwd(idx, dx, dwte, dwpe, M, T, C, V, S(stream));
+}
+
+int abcgpt_layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* y_f32,
+                         float* mean, float* rstd, int M, int C, void* stream) {
+  return layernorm_fwd(x, weight, bias, y_bf16, y_f32, mean, rstd, M, C, S(stream));
+}
+int abcgpt_layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean,
+                         const float* rstd, const float* dresid_in, float* dx_out, void* dx_bf16, float* dweight,
+                         float* dbias, int M, int C, void* stream) {
+  return layernorm_bwd(dy_bf16, x, weight, mean, rstd, dresid_in, dx_out, dx_bf16, dweight, dbias, M, C, S(stream));
+}
+
+int abcgpt_attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, void* stream) {
+  return attn_fwd(qkv, out, lse, B, T, H, S(stream));
+}
+int abcgpt_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                    int B, int T, int H, void* stream) {
+  return attn_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, S(stream));
+}
+
+int abcgpt_ce_fwd(const void* logits, int64_t ldl, const int64_t* targets, float* row_loss, int M, int V,
+                  void* stream) {
+  return ce_fwd(logits, ldl, targets, row_loss, M, V, S(stream));
+}
+int abcgpt_ce_finalize(const float* row_loss, const int64_t* targets, int M, float* loss_sum_count, float* loss,
+                       void* stream) {
+  return ce_finalize(row_loss, targets, M, loss_sum_count, loss, S(stream));
+}
+int abcgpt_ce_bwd(const void* logits, int64_t ldl, const int64_t* targets, const float* loss_sum_count,
+                  const float* grad_loss, void* dlogits, int M, int V, void* stream) {
+  return ce_bwd(logits, ldl, targets, loss_sum_count, grad_loss, dlogits, M, V, S(stream));
+}
+
+int abcgpt_sumsq(const float* g, int64_t n, float* out, void* stream) { return sumsq(g, n, out, S(stream)); }
+int abcgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int step, const float* sumsq_ptr, float max_norm,
+                 void* stream) {
+  return adamw(p, g, m, v, shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, step, sumsq_ptr, max_norm, S(stream));
+}
+int abcgpt_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream) {
+  return cast_f32_to_bf16(x, y_bf16, n, S(stream));
+}
+int abcgpt_argmax(const void* logits, int64_t ldl, int V, int64_t* out, int64_t out_stride, int B, void* stream) {
+  return argmax_rows(logits, ldl, V, out, out_stride, B, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+#include "common.h"
+
+#include <mutex>
+
+namespace abcgpt {
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static CUtensorMapDataType dtype_of(int elem_bytes) {
+  return elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+}
+
+int encode_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                   uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-1, "TMA base pointer must be 16-byte aligned");
+  if ((row_bytes & 15) != 0) return fail(-1, "TMA row pitch must be a multiple of 16 bytes (got %llu)",
+                                         (unsigned long long)row_bytes);
+  if (swizzle128 && box_inner * elem_bytes != 128) return fail(-1, "swizzle128 needs a 128-byte inner box");
+  if (box_inner > 256 || box_outer > 256) return fail(-1, "TMA box dims must be <= 256");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, dtype_of(elem_bytes), 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(1000 + static_cast<int>(r), "cuTensorMapEncodeTiled(2d) failed with CUresult %d (inner=%llu outer=%llu "
+                "pitch=%llu box=%ux%u)", (int)r, (unsigned long long)inner, (unsigned long long)outer,
+                (unsigned long long)row_bytes, box_inner, box_outer);
+  return 0;
+}
+
+int encode_tmap_3d(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                   uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,
+                   bool swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-1, "TMA base pointer must be 16-byte aligned");
+  if ((stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0) return fail(-1, "TMA strides must be multiples of 16 B");
+  if (swizzle128 && box0 * elem_bytes != 128) return fail(-1, "swizzle128 needs a 128-byte inner box");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, dtype_of(elem_bytes), 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(1000 + static_cast<int>(r), "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+}  // namespace abcgpt

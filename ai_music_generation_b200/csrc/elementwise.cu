@@ -1,0 +1,411 @@
+// HBM-bound kernels of the step that are not LayerNorm: embedding gather / scatter, fused softmax
+// cross-entropy for the small ABC vocabulary, gradient sum-of-squares, fused clip + AdamW (+ bf16 weight
+// shadow), casts and the greedy sampling head.  All global traffic is 128-bit where alignment allows.
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace abcgpt {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- embedding (model.py:177-179) ----------------------------------------------------------------------
+__global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float4* __restrict__ wte,
+                                 const float4* __restrict__ wpe, float4* __restrict__ x, long long total, int T,
+                                 int C4, int V) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / C4;
+    const int c = static_cast<int>(i - m * C4);
+    long long tok = __ldg(idx + m);
+    tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+    const int t = static_cast<int>(m % T);
+    const float4 a = __ldg(wte + tok * C4 + c);
+    const float4 b = __ldg(wpe + static_cast<long long>(t) * C4 + c);
+    x[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+// dwpe[t,:] += sum_b dx[b,t,:]  (deterministic: one thread per (t, 4 columns), loops over the batch)
+__global__ void embed_bwd_wpe_kernel(const float4* __restrict__ dx, float4* __restrict__ dwpe, int B, int T, int C4) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(T) * C4) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long stride = static_cast<long long>(T) * C4;
+  for (int b = 0; b < B; ++b) {
+    const float4 v = __ldg(dx + b * stride + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float4 o = dwpe[i];
+  o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+  dwpe[i] = o;
+}
+
+// dwte[idx[m],:] += dx[m,:].  The ABC vocabulary has ~95 rows, so thousands of tokens collide on each row:
+// every block first accumulates ROWS_PER_BLOCK tokens x 128 columns into a shared-memory table (shared
+// atomics), then flushes the touched vocabulary rows with vector reductions.  For large vocabularies
+// (table does not fit) it falls back to direct global vector reductions.
+constexpr int kWteCols = 128;
+__global__ void __launch_bounds__(256)
+embed_bwd_wte_smem_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dx, float* __restrict__ dwte,
+                          int M, int C, int V, int rows_per_block) {
+  extern __shared__ float table[];  // [V][kWteCols]
+  const int col0 = blockIdx.y * kWteCols;
+  const int ncols = min(kWteCols, C - col0);
+  for (int i = threadIdx.x; i < V * kWteCols; i += blockDim.x) table[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int m0 = blockIdx.x * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  for (int m = m0 + warp; m < m1; m += nwarps) {
+    long long tok = __ldg(idx + m);
+    if (tok < 0 || tok >= V) continue;
+    const int c = lane * 4;
+    if (c < ncols) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dx + static_cast<long long>(m) * C + col0 + c));
+      float* t = table + tok * kWteCols + c;
+      atomicAdd(t + 0, v.x); atomicAdd(t + 1, v.y); atomicAdd(t + 2, v.z); atomicAdd(t + 3, v.w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V * (kWteCols / 4); i += blockDim.x) {
+    const int r = i / (kWteCols / 4), c = (i % (kWteCols / 4)) * 4;
+    if (c < ncols) {
+      const float* t = table + r * kWteCols + c;
+      if (t[0] != 0.f || t[1] != 0.f || t[2] != 0.f || t[3] != 0.f)
+        ptx::red_add_v4(dwte + static_cast<long long>(r) * C + col0 + c, t[0], t[1], t[2], t[3]);
+    }
+  }
+}
+__global__ void embed_bwd_wte_direct_kernel(const int64_t* __restrict__ idx, const float4* __restrict__ dx,
+                                            float* __restrict__ dwte, long long total, int C4, int V) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / C4;
+    const int c = static_cast<int>(i - m * C4);
+    const long long tok = __ldg(idx + m);
+    if (tok < 0 || tok >= V) continue;
+    const float4 v = __ldg(dx + i);
+    ptx::red_add_v4(dwte + (tok * C4 + c) * 4, v.x, v.y, v.z, v.w);
+  }
+}
+
+// ---- fused softmax cross-entropy (model.py:187) ------------------------------------------------------------
+// one warp per row; logits are bf16 (the autocast lm_head output), the softmax runs in fp32 like
+// F.cross_entropy under autocast.
+__global__ void __launch_bounds__(256)
+ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl, const int64_t* __restrict__ targets,
+              float* __restrict__ row_loss, int M, int V) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const long long tgt = __ldg(targets + row);
+  const __nv_bfloat16* lr = logits + static_cast<long long>(row) * ldl;
+  float mx = -INFINITY;
+  for (int c = lane; c < V; c += 32) mx = fmaxf(mx, __bfloat162float(lr[c]));
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int c = lane; c < V; c += 32) s += __expf(__bfloat162float(lr[c]) - mx);
+  s = warp_sum(s);
+  if (lane == 0) {
+    float l = 0.f;
+    if (tgt >= 0 && tgt < V) l = (mx + __logf(s)) - __bfloat162float(lr[tgt]);
+    row_loss[row] = l;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+ce_finalize_kernel(const float* __restrict__ row_loss, const int64_t* __restrict__ targets, int M,
+                   float* __restrict__ sum_count, float* __restrict__ loss) {
+  __shared__ float ssum[32];
+  __shared__ float scnt[32];
+  float s = 0.f, n = 0.f;
+  // fixed assignment of rows to threads => bitwise reproducible loss
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const long long t = __ldg(targets + i);
+    if (t >= 0) {
+      s += row_loss[i];
+      n += 1.f;
+    }
+  }
+  s = warp_sum(s);
+  n = warp_sum(n);
+  if ((threadIdx.x & 31) == 0) {
+    ssum[threadIdx.x >> 5] = s;
+    scnt[threadIdx.x >> 5] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = ssum[threadIdx.x];
+    n = scnt[threadIdx.x];
+    s = warp_sum(s);
+    n = warp_sum(n);
+    if (threadIdx.x == 0) {
+      sum_count[0] = s;
+      sum_count[1] = n;
+      if (loss) loss[0] = s / n;  // all-ignored batch -> nan, like F.cross_entropy
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl, const int64_t* __restrict__ targets,
+              const float* __restrict__ sum_count, const float* __restrict__ grad_loss,
+              __nv_bfloat16* __restrict__ dlogits, int M, int V) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const long long tgt = __ldg(targets + row);
+  const __nv_bfloat16* lr = logits + static_cast<long long>(row) * ldl;
+  __nv_bfloat16* dr = dlogits + static_cast<long long>(row) * ldl;
+  const bool valid = tgt >= 0 && tgt < V;
+  const float scale = valid ? __ldg(grad_loss) / __ldg(sum_count + 1) : 0.f;
+  float mx = -INFINITY;
+  for (int c = lane; c < V; c += 32) mx = fmaxf(mx, __bfloat162float(lr[c]));
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int c = lane; c < V; c += 32) s += __expf(__bfloat162float(lr[c]) - mx);
+  s = warp_sum(s);
+  const float inv = 1.0f / s;
+  for (int c = lane; c < static_cast<int>(ldl); c += 32) {
+    float g = 0.f;
+    if (c < V && valid) {
+      const float p = __expf(__bfloat162float(lr[c]) - mx) * inv;
+      g = (p - (c == tgt ? 1.f : 0.f)) * scale;
+    }
+    dr[c] = __float2bfloat16_rn(g);
+  }
+}
+
+// ---- gradient norm, clip + AdamW (train.py:350-354; torch.optim.AdamW single-tensor formulas) -----------------
+__global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  __shared__ float sh[16];
+  float s = 0.f;
+  const long long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(g4 + i);
+    s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = g[(n4 << 2) + threadIdx.x];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+struct AdamArgs {
+  float lr, beta1, beta2, eps, wd, step_size, inv_bc2_sqrt, max_norm;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float gscale) {
+  g *= gscale;
+  p *= (1.0f - a.lr * a.wd);
+  m = m + (1.0f - a.beta1) * (g - m);                 // lerp(m, g, 1-beta1)
+  v = a.beta2 * v + (1.0f - a.beta2) * g * g;
+  const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
+  p -= a.step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(512)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             __nv_bfloat16* __restrict__ shadow, long long n, AdamArgs a, const float* __restrict__ sumsq) {
+  float gscale = 1.0f;
+  if (sumsq != nullptr) {
+    const float norm = sqrtf(__ldg(sumsq));
+    gscale = fminf(1.0f, a.max_norm / (norm + 1e-6f));
+  }
+  const long long n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = __ldg(g4 + i);
+    adam_one(pp.x, gg.x, mm.x, vv.x, a, gscale);
+    adam_one(pp.y, gg.y, mm.y, vv.y, a, gscale);
+    adam_one(pp.z, gg.z, mm.z, vv.z, a, gscale);
+    adam_one(pp.w, gg.w, mm.w, vv.w, a, gscale);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(ptx::pack_bf16x2(pp.x, pp.y), ptx::pack_bf16x2(pp.z, pp.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam_one(pp, g[i], mm, vv, a, gscale);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pp);
+  }
+}
+
+__global__ void __launch_bounds__(512) cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(ptx::pack_bf16x2(v.x, v.y), ptx::pack_bf16x2(v.z, v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    y[i] = __float2bfloat16_rn(x[i]);
+  }
+}
+
+// ---- greedy head (model.py:316-328 with top_k=1) -----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+argmax_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl, int V, int64_t* __restrict__ out,
+              long long out_stride, int B) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const __nv_bfloat16* lr = logits + static_cast<long long>(row) * ldl;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < V; c += 32) {
+    const float x = __bfloat162float(lr[c]);
+    if (x > best) { best = x; bi = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) out[static_cast<long long>(row) * out_stride] = bi;
+}
+
+inline int grid_for(long long work_items, int threads, int waves = 8) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+int embed_fwd(const int64_t* idx, const float* wte, const float* wpe, float* x, int M, int T, int C, int V,
+              cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(idx && wte && wpe && x, "embed_fwd: null pointer");
+  ABCGPT_CHECK_ARG(M > 0 && T > 0 && C % 4 == 0 && V > 0, "embed_fwd: bad shape M=%d T=%d C=%d V=%d", M, T, C, V);
+  const long long total = static_cast<long long>(M) * (C / 4);
+  embed_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(idx, reinterpret_cast<const float4*>(wte),
+                                                             reinterpret_cast<const float4*>(wpe),
+                                                             reinterpret_cast<float4*>(x), total, T, C / 4, V);
+  return launch_status("embed_fwd_kernel");
+}
+
+int embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int M, int T, int C, int V,
+              cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(idx && dx && dwte && dwpe, "embed_bwd: null pointer");
+  ABCGPT_CHECK_ARG(M > 0 && T > 0 && M % T == 0 && C % 4 == 0 && V > 0, "embed_bwd: bad shape M=%d T=%d C=%d V=%d", M, T, C, V);
+  const int C4 = C / 4;
+  {
+    const long long n = static_cast<long long>(T) * C4;
+    embed_bwd_wpe_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, stream>>>(
+        reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dwpe), M / T, T, C4);
+    int rc = launch_status("embed_bwd_wpe_kernel");
+    if (rc) return rc;
+  }
+  const size_t table_bytes = static_cast<size_t>(V) * kWteCols * sizeof(float);
+  if (table_bytes <= 96 * 1024) {
+    static bool done = false;
+    if (!done) {
+      ABCGPT_CUDA(cudaFuncSetAttribute(embed_bwd_wte_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      done = true;
+    }
+    const int rows_per_block = 512;
+    dim3 grid((M + rows_per_block - 1) / rows_per_block, (C + kWteCols - 1) / kWteCols);
+    embed_bwd_wte_smem_kernel<<<grid, 256, table_bytes, stream>>>(idx, dx, dwte, M, C, V, rows_per_block);
+    return launch_status("embed_bwd_wte_smem_kernel");
+  }
+  const long long total = static_cast<long long>(M) * C4;
+  embed_bwd_wte_direct_kernel<<<grid_for(total, 256), 256, 0, stream>>>(idx, reinterpret_cast<const float4*>(dx), dwte,
+                                                                        total, C4, V);
+  return launch_status("embed_bwd_wte_direct_kernel");
+}
+
+int ce_fwd(const void* logits, long long ldl, const int64_t* targets, float* row_loss, int M, int V,
+           cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(logits && targets && row_loss && M > 0 && V > 0 && ldl >= V, "ce_fwd: bad arguments");
+  ce_fwd_kernel<<<(M + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ldl, targets, row_loss,
+                                                 M, V);
+  return launch_status("ce_fwd_kernel");
+}
+int ce_finalize(const float* row_loss, const int64_t* targets, int M, float* loss_sum_count, float* loss,
+                cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(row_loss && targets && loss_sum_count && M > 0, "ce_finalize: bad arguments");
+  ce_finalize_kernel<<<1, 1024, 0, stream>>>(row_loss, targets, M, loss_sum_count, loss);
+  return launch_status("ce_finalize_kernel");
+}
+int ce_bwd(const void* logits, long long ldl, const int64_t* targets, const float* loss_sum_count,
+           const float* grad_loss, void* dlogits, int M, int V, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(logits && targets && loss_sum_count && grad_loss && dlogits && M > 0 && V > 0 && ldl >= V,
+                   "ce_bwd: bad arguments");
+  ce_bwd_kernel<<<(M + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ldl, targets,
+                                                 loss_sum_count, grad_loss, reinterpret_cast<__nv_bfloat16*>(dlogits), M,
+                                                 V);
+  return launch_status("ce_bwd_kernel");
+}
+
+int sumsq(const float* g, long long n, float* out, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(g && out && n > 0, "sumsq: bad arguments");
+  ABCGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: pointer must be 16-byte aligned");
+  sumsq_kernel<<<grid_for(n / 4 + 1, 512, 4), 512, 0, stream>>>(g, n, out);
+  return launch_status("sumsq_kernel");
+}
+
+int adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
+          float beta2, float eps, float weight_decay, int step, const float* sumsq_ptr, float max_norm,
+          cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
+  ABCGPT_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0,
+                   "adamw: arenas must be 16-byte aligned");
+  AdamArgs a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.max_norm = max_norm;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  a.step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  a.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+  adamw_kernel<<<grid_for(n / 4 + 1, 512, 4), 512, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16),
+                                                                n, a, sumsq_ptr);
+  return launch_status("adamw_kernel");
+}
+
+int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(x && y && n > 0, "cast: bad arguments");
+  ABCGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+                   "cast: pointers must be 16/8-byte aligned");
+  cast_kernel<<<grid_for(n / 4 + 1, 512, 4), 512, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
+  return launch_status("cast_kernel");
+}
+
+int argmax_rows(const void* logits, long long ldl, int V, int64_t* out, long long out_stride, int B,
+                cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(logits && out && V > 0 && B > 0, "argmax: bad arguments");
+  argmax_kernel<<<(B + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ldl, V, out, out_stride, B);
+  return launch_status("argmax_kernel");
+}
+
+}  // namespace abcgpt

@@ -1,0 +1,218 @@
+// LayerNorm forward / backward (nanoGPT/model.py:18-27: F.layer_norm(x, (C,), weight, bias, 1e-5)).
+//
+// HBM-bound: one warp owns one row, the row lives in registers (C/128 float4 per lane), all global traffic
+// is 128-bit and coalesced, reductions are warp shuffles.  The forward emits the bf16 copy the next GEMM
+// consumes (the reference rounds the fp32 LN output to bf16 at the autocast boundary of nn.Linear), the
+// backward fuses the residual-gradient add and emits both the fp32 stream gradient and its bf16 copy.
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace abcgpt {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NV>  // NV float4 per lane: C <= NV*128
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+              __nv_bfloat16* __restrict__ y, float* __restrict__ yf, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, int M, int C) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    v[i] = (idx < nvec) ? __ldg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / static_cast<float>(C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + bq * bq) + (c * c + d * d);
+    }
+  }
+  const float var = warp_sum(ss) / static_cast<float>(C);
+  const float rstd = rsqrtf(var + 1e-5f);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  uint2* yr = y ? reinterpret_cast<uint2*>(y + static_cast<long long>(row) * C) : nullptr;
+  float4* yfr = yf ? reinterpret_cast<float4*>(yf + static_cast<long long>(row) * C) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w) + idx);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x;
+      o.y = (v[i].y - mean) * rstd * g.y;
+      o.z = (v[i].z - mean) * rstd * g.z;
+      o.w = (v[i].w - mean) * rstd * g.w;
+      if (b) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + idx);
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+      }
+      if (yr) yr[idx] = make_uint2(ptx::pack_bf16x2(o.x, o.y), ptx::pack_bf16x2(o.z, o.w));
+      if (yfr) yfr[idx] = o;
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+              float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ dw, float* __restrict__ db,
+              int M, int C) {
+  extern __shared__ float red[];  // [kWarpsPerBlock][C] reused for dweight then dbias
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nvec = C >> 2;
+  float4 gw[NV], accw[NV], accb[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    gw[i] = (idx < nvec) ? __ldg(reinterpret_cast<const float4*>(w) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    accw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    accb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invC = 1.0f / static_cast<float>(C);
+  for (int row = blockIdx.x * kWarpsPerBlock + warp; row < M; row += gridDim.x * kWarpsPerBlock) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+    const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<long long>(row) * C);
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        const float4 xv = __ldg(xr + idx);
+        const uint2 d = __ldg(dyr + idx);
+        const float4 dyv = make_float4(ptx::bf16lo(d.x), ptx::bf16hi(d.x), ptx::bf16lo(d.y), ptx::bf16hi(d.y));
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[i] = make_float4(dyv.x * gw[i].x, dyv.y * gw[i].y, dyv.z * gw[i].z, dyv.w * gw[i].w);
+        s1 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+        s2 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        accw[i].x += dyv.x * xh[i].x; accw[i].y += dyv.y * xh[i].y;
+        accw[i].z += dyv.z * xh[i].z; accw[i].w += dyv.w * xh[i].w;
+        accb[i].x += dyv.x; accb[i].y += dyv.y; accb[i].z += dyv.z; accb[i].w += dyv.w;
+      } else {
+        xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g[i] = xh[i];
+      }
+    }
+    const float c1 = warp_sum(s1) * invC;
+    const float c2 = warp_sum(s2) * invC;
+    float4* dxr = reinterpret_cast<float4*>(dx + static_cast<long long>(row) * C);
+    const float4* drr = dres ? reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * C) : nullptr;
+    uint2* dxbr = dxb ? reinterpret_cast<uint2*>(dxb + static_cast<long long>(row) * C) : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        float4 o;
+        o.x = (g[i].x - c2 - xh[i].x * c1) * rs;
+        o.y = (g[i].y - c2 - xh[i].y * c1) * rs;
+        o.z = (g[i].z - c2 - xh[i].z * c1) * rs;
+        o.w = (g[i].w - c2 - xh[i].w * c1) * rs;
+        if (drr) {
+          const float4 r = __ldg(drr + idx);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        dxr[idx] = o;
+        if (dxbr) dxbr[idx] = make_uint2(ptx::pack_bf16x2(o.x, o.y), ptx::pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
+  // block-level reduction of the per-warp dweight / dbias partials, then one atomic per column per block
+  float4* redv = reinterpret_cast<float4*>(red);
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? dw : db;
+    if (dst == nullptr) continue;  // uniform across the block
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) redv[warp * nvec + idx] = pass == 0 ? accw[i] : accb[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kWarpsPerBlock; ++ww) s += red[ww * C + c];
+      atomicAdd(dst + c, s);
+    }
+  }
+}
+
+}  // namespace
+
+#define LN_DISPATCH(NVV, ...) \
+  switch (NVV) {              \
+    case 1: { constexpr int NV = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int NV = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int NV = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int NV = 4; __VA_ARGS__; } break; \
+    case 5: { constexpr int NV = 5; __VA_ARGS__; } break; \
+    case 6: { constexpr int NV = 6; __VA_ARGS__; } break; \
+    case 7: { constexpr int NV = 7; __VA_ARGS__; } break; \
+    case 8: { constexpr int NV = 8; __VA_ARGS__; } break; \
+    case 9: case 10: case 11: case 12: { constexpr int NV = 12; __VA_ARGS__; } break; \
+    default: { constexpr int NV = 16; __VA_ARGS__; } break; \
+  }
+
+int layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* y_f32, float* mean,
+                  float* rstd, int M, int C, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0 && C <= 2048, "layernorm: need C %% 4 == 0 and C <= 2048 (got %d)", C);
+  ABCGPT_CHECK_ARG(x && weight && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
+  const int nv = (C + 127) / 128;
+  const int grid = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  LN_DISPATCH(nv, (ln_fwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+                      x, weight, bias, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, C)));
+  return launch_status("ln_fwd_kernel");
+}
+
+int layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean, const float* rstd,
+                  const float* dresid_in, float* dx_out, void* dx_bf16, float* dweight, float* dbias, int M, int C,
+                  cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0 && C <= 2048, "layernorm: need C %% 4 == 0 and C <= 2048 (got %d)", C);
+  ABCGPT_CHECK_ARG(dy_bf16 && x && weight && mean && rstd && dx_out, "layernorm_bwd: null pointer");
+  const int nv = (C + 127) / 128;
+  int grid = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int cap = sm_count() * 4;
+  if (grid > cap) grid = cap;
+  const size_t smem = static_cast<size_t>(kWarpsPerBlock) * C * sizeof(float);
+  LN_DISPATCH(nv, {
+    if (smem > 48 * 1024) {
+      static bool done = false;
+      if (!done) {
+        ABCGPT_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        done = true;
+      }
+    }
+    ln_bwd_kernel<NV><<<grid, kWarpsPerBlock * 32, smem, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, weight, mean, rstd, dresid_in, dx_out,
+        reinterpret_cast<__nv_bfloat16*>(dx_bf16), dweight, dbias, M, C);
+  });
+  return launch_status("ln_bwd_kernel");
+}
+
+}  // namespace abcgpt

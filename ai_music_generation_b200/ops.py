@@ -1,0 +1,136 @@
+"""Tensor-level wrappers over the C ABI: torch supplies device memory and the stream, nothing else.
+
+Every function enqueues hand-written sm_100a kernels on torch's current CUDA stream through libabcgpt.so and
+raises AbcgptError on failure.  No function here computes anything with torch ops.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _C
+from ._C import EPI_BF16, EPI_DGELU, EPI_F32, EPI_F32_RED, EPI_GELU, EPI_RESID  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise _C.AbcgptError(f"{name}: expected a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise _C.AbcgptError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def _rowmajor_ld(t, name):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _C.AbcgptError(f"{name}: expected a 2-D tensor with unit inner stride, got strides {t.stride()}")
+    return t.stride(0)
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_BF16, out=None, out2=None, aux=None,
+         bias=None, tile_n=0, splits=0):
+    """out[M,N] = sum_k A[m,k] B[n,k] (bf16 in, fp32 accumulate on tcgen05).
+
+    a: [M,K] (a_mn=False) or stored [K,M] (a_mn=True); b: [N,K] or stored [K,N]."""
+    _chk(a, torch.bfloat16, "gemm a")
+    _chk(b, torch.bfloat16, "gemm b")
+    lda, ldb = _rowmajor_ld(a, "gemm a"), _rowmajor_ld(b, "gemm b")
+    Ma, Ka = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    Nb, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    M = Ma if M is None else M
+    N = Nb if N is None else N
+    K = Ka if K is None else K
+    if Ka != Kb and (K is None):
+        raise _C.AbcgptError(f"gemm: contraction mismatch {Ka} vs {Kb}")
+    ldc = _rowmajor_ld(out, "gemm out")
+    ldc2 = _rowmajor_ld(out2, "gemm out2") if out2 is not None else 0
+    ldaux = _rowmajor_ld(aux, "gemm aux") if aux is not None else 0
+    if bias is not None:
+        _chk(bias, torch.float32, "gemm bias")
+    rc = _C.lib().abcgpt_gemm_bf16(a.data_ptr(), int(a_mn), lda, b.data_ptr(), int(b_mn), ldb, M, N, K, epilogue,
+                                  out.data_ptr(), ldc, _ptr(out2), ldc2, _ptr(aux), ldaux, _ptr(bias), tile_n, splits,
+                                  _stream())
+    _C.check(rc, "abcgpt_gemm_bf16")
+    return out
+
+
+def embed_fwd(idx, wte, wpe, x, T):
+    _chk(idx, torch.int64, "embed idx")
+    M = idx.numel()
+    V, C = wte.shape
+    _C.check(_C.lib().abcgpt_embed_fwd(idx.data_ptr(), wte.data_ptr(), wpe.data_ptr(), x.data_ptr(), M, T, C, V, _stream()),
+             "abcgpt_embed_fwd")
+    return x
+
+
+def embed_bwd(idx, dx, dwte, dwpe, T):
+    M = idx.numel()
+    V, C = dwte.shape
+    _C.check(_C.lib().abcgpt_embed_bwd(idx.data_ptr(), dx.data_ptr(), dwte.data_ptr(), dwpe.data_ptr(), M, T, C, V, _stream()),
+             "abcgpt_embed_bwd")
+
+
+def layernorm_fwd(x, weight, bias, y_bf16, mean, rstd, y_f32=None):
+    _chk(x, torch.float32, "layernorm x")
+    M, C = x.shape
+    _C.check(_C.lib().abcgpt_layernorm_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(y_bf16), _ptr(y_f32),
+                                          _ptr(mean), _ptr(rstd), M, C, _stream()), "abcgpt_layernorm_fwd")
+
+
+def layernorm_bwd(dy_bf16, x, weight, mean, rstd, dresid_in, dx_out, dx_bf16, dweight, dbias):
+    M, C = x.shape
+    _C.check(_C.lib().abcgpt_layernorm_bwd(dy_bf16.data_ptr(), x.data_ptr(), weight.data_ptr(), mean.data_ptr(),
+                                          rstd.data_ptr(), _ptr(dresid_in), dx_out.data_ptr(), _ptr(dx_bf16),
+                                          _ptr(dweight), _ptr(dbias), M, C, _stream()), "abcgpt_layernorm_bwd")
+
+
+def attn_fwd(qkv, out, lse, B, T, H):
+    _chk(qkv, torch.bfloat16, "attn qkv")
+    _C.check(_C.lib().abcgpt_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, H, _stream()),
+             "abcgpt_attn_fwd")
+
+
+def attn_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H):
+    _C.check(_C.lib().abcgpt_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                     dqkv.data_ptr(), B, T, H, _stream()), "abcgpt_attn_bwd")
+
+
+def ce_fwd(logits, targets, row_loss, sum_count, loss, V):
+    _chk(logits, torch.bfloat16, "ce logits")
+    _chk(targets, torch.int64, "ce targets")
+    M, ldl = logits.shape[0], logits.stride(0)
+    L = _C.lib()
+    _C.check(L.abcgpt_ce_fwd(logits.data_ptr(), ldl, targets.data_ptr(), row_loss.data_ptr(), M, V, _stream()),
+             "abcgpt_ce_fwd")
+    _C.check(L.abcgpt_ce_finalize(row_loss.data_ptr(), targets.data_ptr(), M, sum_count.data_ptr(), _ptr(loss), _stream()),
+             "abcgpt_ce_finalize")
+
+
+def ce_bwd(logits, targets, sum_count, grad_loss, dlogits, V):
+    M, ldl = logits.shape[0], logits.stride(0)
+    _C.check(_C.lib().abcgpt_ce_bwd(logits.data_ptr(), ldl, targets.data_ptr(), sum_count.data_ptr(), grad_loss.data_ptr(),
+                                   dlogits.data_ptr(), M, V, _stream()), "abcgpt_ce_bwd")
+
+
+def sumsq(g, out):
+    _C.check(_C.lib().abcgpt_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "abcgpt_sumsq")
+
+
+def adamw(p, g, m, v, shadow, *, lr, beta1, beta2, eps, weight_decay, step, sumsq=None, max_norm=0.0):
+    _C.check(_C.lib().abcgpt_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), p.numel(),
+                                  lr, beta1, beta2, eps, weight_decay, step, _ptr(sumsq), max_norm, _stream()),
+             "abcgpt_adamw")
+
+
+def cast_bf16(x, y):
+    _C.check(_C.lib().abcgpt_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "abcgpt_cast_f32_to_bf16")
+
+
+def argmax(logits, V, out, out_stride=1):
+    B, ldl = logits.shape[0], logits.stride(0)
+    _C.check(_C.lib().abcgpt_argmax(logits.data_ptr(), ldl, V, out.data_ptr(), out_stride, B, _stream()), "abcgpt_argmax")
