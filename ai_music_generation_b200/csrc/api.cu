@@ -68,6 +68,9 @@ int abcgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16
 int abcgpt_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream) {
   return cast_f32_to_bf16(x, y_bf16, n, S(stream));
 }
+int abcgpt_colsum_bf16(const void* dy, int64_t ld, int M, int N, float* out, void* stream) {
+  return colsum_bf16(dy, ld, M, N, out, S(stream));
+}
 int abcgpt_argmax(const void* logits, int64_t ldl, int V, int64_t* out, int64_t out_stride, int B, void* stream) {
   return argmax_rows(logits, ldl, V, out, out_stride, B, S(stream));
 }

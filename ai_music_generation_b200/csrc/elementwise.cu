@@ -271,6 +271,35 @@ __global__ void __launch_bounds__(512) cast_kernel(const float* __restrict__ x, 
   }
 }
 
+
+// ---- bias gradient: out[n] += sum_m dy[m,n]  (bf16 in, fp32 accumulate; only used when config.bias=True) ----
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, int M, int N, int rows_per_block,
+              float* __restrict__ out) {
+  __shared__ float sh[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 64 + lane * 2;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float a0 = 0.f, a1 = 0.f;
+  if (col < N) {
+    for (int m = m0 + warp; m < m1; m += 8) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(dy + static_cast<long long>(m) * ld + col));
+      a0 += ptx::bf16lo(v);
+      a1 += ptx::bf16hi(v);
+    }
+  }
+  sh[warp][lane * 2] = a0;
+  sh[warp][lane * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < N) atomicAdd(out + c, s);
+  }
+}
+
 // ---- greedy head (model.py:316-328 with top_k=1) -----------------------------------------------------------
 __global__ void __launch_bounds__(256)
 argmax_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl, int V, int64_t* __restrict__ out,
@@ -399,6 +428,14 @@ int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream) 
                    "cast: pointers must be 16/8-byte aligned");
   cast_kernel<<<grid_for(n / 4 + 1, 512, 4), 512, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
   return launch_status("cast_kernel");
+}
+
+int colsum_bf16(const void* dy, long long ld, int M, int N, float* out, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(dy && out && M > 0 && N > 0 && N % 2 == 0 && ld % 2 == 0, "colsum: bad arguments");
+  const int rows_per_block = 1024;
+  dim3 grid((N + 63) / 64, (M + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld, M, N, rows_per_block, out);
+  return launch_status("colsum_kernel");
 }
 
 int argmax_rows(const void* logits, long long ldl, int V, int64_t* out, long long out_stride, int B,

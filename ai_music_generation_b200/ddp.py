@@ -1,0 +1,137 @@
+"""Data-parallel wrapper for GPT (reference: torch DDP at nanoGPT/train.py:226-227, the
+`model.require_backward_grad_sync` toggle at :341 and `raw_model = model.module` at :279).
+
+One process per GPU (torchrun).  Gradients already live in one flat fp32 arena, so a bucket is a slice: no
+flatten/copy kernels.  Buckets follow the order in which the backward plan completes layers (last block
+first); each bucket's all-reduce (average) is enqueued on a side stream as soon as its last layer's wgrad
+has been launched, overlapping NCCL over NVLink with the remaining backward.  The embedding / lm_head tensor
+and the 1-D parameters finish last and form the final bucket.  `wait()` makes the compute stream wait for the
+outstanding collectives (device-side; no host sync) before clip / AdamW.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def plan_buckets(layer_ranges, head_range, tail_range, bucket_elems):
+    """Groups per-layer [lo, hi) element ranges of the flat gradient arena into all-reduce buckets.
+
+    layer_ranges[i] is the contiguous range of block i's 2-D gradients; ranges are adjacent and ascending.
+    Returns [(trigger_layer, lo, hi)] in launch order (trigger_layer = the layer whose completion releases the
+    bucket; -1 for the final bucket(s) released when the whole backward is done)."""
+    buckets = []
+    hi = None
+    lo = None
+    for li in range(len(layer_ranges) - 1, -1, -1):
+        l_lo, l_hi = layer_ranges[li]
+        if hi is None:
+            hi = l_hi
+        lo = l_lo
+        if hi - lo >= bucket_elems or li == 0:
+            buckets.append((li, lo, hi))
+            hi = None
+    if head_range[1] > head_range[0]:
+        buckets.append((-1, head_range[0], head_range[1]))
+    if tail_range[1] > tail_range[0]:
+        buckets.append((-1, tail_range[0], tail_range[1]))
+    return buckets
+
+
+class GradSync:
+    def __init__(self, grad_flat, layer_ranges, head_range, tail_range, process_group=None, bucket_mb=64.0):
+        self.grad = grad_flat
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.buckets = plan_buckets(layer_ranges, head_range, tail_range, int(bucket_mb * 1024 * 1024 / 4))
+        self._by_trigger = {}
+        for b in self.buckets:
+            self._by_trigger.setdefault(b[0], []).append(b)
+        self.cuda = grad_flat.is_cuda
+        self.comm_stream = torch.cuda.Stream(device=grad_flat.device) if self.cuda else None
+        self._pending = []
+        self.launched = []  # (lo, hi) in launch order, for tests
+
+    def _launch(self, bucket):
+        _, lo, hi = bucket
+        view = self.grad[lo:hi]
+        self.launched.append((lo, hi))
+        if self.world == 1:
+            return
+        if self.cuda:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ready)
+                work = dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self._pending.append(work)
+        else:  # gloo on CPU (tests): no AVG reduction there
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+            view.div_(self.world)
+
+    def layer_done(self, li):
+        for b in self._by_trigger.get(li, ()):
+            self._launch(b)
+
+    def backward_done(self):
+        for b in self._by_trigger.get(-1, ()):
+            self._launch(b)
+
+    def wait(self):
+        for w in self._pending:
+            w.wait()  # NCCL: the current stream waits for the collective; the host does not block
+        self._pending = []
+        self.launched = []
+
+
+class DDP(torch.nn.Module):
+    """Thin container with the two attributes the reference's training loop touches."""
+
+    def __init__(self, module, device_ids=None, process_group=None, bucket_mb=64.0):
+        super().__init__()
+        self.module = module
+        self._process_group = process_group
+        self._bucket_mb = bucket_mb
+        self._sync_for = None
+        if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            flat = module._arena["flat"]
+            dist.broadcast(flat, src=0, group=process_group)  # same start on every rank, like DDP's constructor
+            module._shadow_fresh = False
+
+    @property
+    def require_backward_grad_sync(self):
+        return self.module.require_backward_grad_sync
+
+    @require_backward_grad_sync.setter
+    def require_backward_grad_sync(self, value):
+        self.module.require_backward_grad_sync = bool(value)
+
+    def _ensure_sync(self):
+        m = self.module
+        m._ensure_device_state()
+        a = m._arena
+        key = a["grad"].data_ptr()
+        if self._sync_for == key:
+            return
+        names, offs, params = a["names"], a["offs"], a["params"]
+        end = {n: o + ((p.numel() + 7) // 8) * 8 for n, o, p in zip(names, offs, params)}
+        start = dict(zip(names, offs))
+        layer_ranges = []
+        for i in range(m.config.n_layer):
+            pre = f"transformer.h.{i}."
+            layer_ranges.append((start[pre + "attn.c_attn.weight"], end[pre + "mlp.c_proj.weight"]))
+        head = (0, layer_ranges[0][0]) if layer_ranges else (0, a["n_decay"])
+        tail = (a["n_decay"], a["total"])
+        m._grad_sync = GradSync(a["grad"], layer_ranges, head, tail, self._process_group, self._bucket_mb)
+        self._sync_for = key
+
+    def forward(self, *args, **kwargs):
+        if dist.is_initialized():
+            self._ensure_sync()
+        return self.module(*args, **kwargs)
+
+    def parameters(self, recurse=True):
+        return self.module.parameters(recurse)
+
+    def clip_grad_norm_(self, max_norm):
+        return self.module.clip_grad_norm_(max_norm)

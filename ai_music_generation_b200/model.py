@@ -1,0 +1,468 @@
+"""GPT(GPTConfig) — drop-in for the reference's nanoGPT/model.py on B200 (sm_100a).
+
+Same call surface as the reference (GPTConfig :108-116, GPT.forward :170-193, configure_optimizers :263-287,
+generate :305-330, estimate_mfu :289-303, crop_block_size :195-204, get_num_params :150-160) and the same
+parameter names / shapes / init RNG consumption, so reference checkpoints load and `train.py` / `sample.py` /
+`bench.py` style drivers run unchanged.  What differs is everything underneath:
+
+  * parameters live in ONE flat fp32 arena (and gradients, Adam moments and the bf16 GEMM-operand shadow in
+    matching arenas); nn.Parameters are views, so clip + AdamW are single fused launches and DDP buckets are
+    plain slices (no copies);
+  * GPT.forward / backward are a fixed launch plan of hand-written sm_100a kernels from libabcgpt.so over
+    pre-allocated activation buffers (no per-step allocation, CUDA-graph capturable), exposed to autograd as
+    one Function: `loss.backward()` fills `.grad` on `model.parameters()` exactly like the reference;
+  * the dtype flow is the one the reference gets under torch.autocast(bfloat16) (fp32 residual stream,
+    LayerNorm and loss; bf16 GEMM/attention operands with fp32 accumulation), whether or not the caller
+    opens an autocast context.
+
+There is no CPU or eager-PyTorch fallback: a missing extension or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from . import _C, ops
+from .optim import FusedAdamW
+
+
+@dataclass
+class GPTConfig:
+    block_size: int = 1024
+    vocab_size: int = 50304
+    n_layer: int = 12
+    n_head: int = 12
+    n_embd: int = 768
+    dropout: float = 0.0
+    bias: bool = True
+
+
+# The sub-modules below only own parameters (names / shapes / init identical to the reference); the arithmetic of
+# the whole network is scheduled by GPT._forward_plan / GPT._backward_plan.
+class LayerNorm(nn.Module):
+    def __init__(self, ndim, bias):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(ndim))
+        self.bias = nn.Parameter(torch.zeros(ndim)) if bias else None
+
+
+class CausalSelfAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        assert config.n_embd % config.n_head == 0
+        self.c_attn = nn.Linear(config.n_embd, 3 * config.n_embd, bias=config.bias)
+        self.c_proj = nn.Linear(config.n_embd, config.n_embd, bias=config.bias)
+        self.attn_dropout = nn.Dropout(config.dropout)
+        self.resid_dropout = nn.Dropout(config.dropout)
+        self.n_head, self.n_embd, self.dropout = config.n_head, config.n_embd, config.dropout
+
+
+class MLP(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.c_fc = nn.Linear(config.n_embd, 4 * config.n_embd, bias=config.bias)
+        self.gelu = nn.GELU()
+        self.c_proj = nn.Linear(4 * config.n_embd, config.n_embd, bias=config.bias)
+        self.dropout = nn.Dropout(config.dropout)
+
+
+class Block(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.ln_1 = LayerNorm(config.n_embd, bias=config.bias)
+        self.attn = CausalSelfAttention(config)
+        self.ln_2 = LayerNorm(config.n_embd, bias=config.bias)
+        self.mlp = MLP(config)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _Buffers:
+    """Activation / scratch buffers for one (B, T) shape, allocated once and reused every step."""
+
+    def __init__(self, cfg: GPTConfig, B: int, T: int, device, keep_activations: bool):
+        M, C, L, H = B * T, cfg.n_embd, cfg.n_layer, cfg.n_head
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *s, dt=bf: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
+        nl = L if keep_activations else 1
+        self.B, self.T, self.M = B, T, M
+        self.keep = keep_activations
+        self.Vpad = _round_up(cfg.vocab_size, 128) if cfg.vocab_size <= 1024 else _round_up(cfg.vocab_size, 8)
+        self.x = [e(M, C, dt=f32) for _ in range(nl + 1)]        # residual stream at each block input (+ final)
+        self.xmid = [e(M, C, dt=f32) for _ in range(nl)]         # after the attention residual
+        self.ln1 = [e(M, C) for _ in range(nl)]
+        self.ln2 = [e(M, C) for _ in range(nl)]
+        self.stat = [e(4, M, dt=f32) for _ in range(nl)]          # mean1, rstd1, mean2, rstd2
+        self.qkv = [e(M, 3 * C) for _ in range(nl)]
+        self.att = [e(M, C) for _ in range(nl)]
+        self.lse = [e(B, H, T, dt=f32) for _ in range(nl)]
+        self.h = [e(M, 4 * C) for _ in range(nl)]
+        self.g = [e(M, 4 * C) for _ in range(nl)]
+        self.lnf = e(M, C)
+        self.statf = e(2, M, dt=f32)
+        self.logits = e(M, self.Vpad)
+        self.row_loss = e(M, dt=f32)
+        self.sum_count = e(2, dt=f32)
+        self.loss = e(1, dt=f32)
+        self.last_logits = e(B, self.Vpad)
+        if keep_activations:
+            self.dx = [e(M, C, dt=f32) for _ in range(2)]
+            self.dxb = e(M, C)
+            self.dln = e(M, C)
+            self.datt = e(M, C)
+            self.dqkv = e(M, 3 * C)
+            self.dh = e(M, 4 * C)
+            self.delta = e(B, H, T, dt=f32)
+            self.dlogits = e(M, self.Vpad)
+
+
+class _GPTStep(torch.autograd.Function):
+    """One autograd node for the whole network: forward launches the forward plan, backward the backward plan."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, idx, targets):
+        bufs = model._forward_plan(idx, targets, keep_activations=True)
+        ctx.model, ctx.bufs, ctx.idx, ctx.targets = model, bufs, idx, targets
+        B, T = idx.shape
+        logits = bufs.logits.view(B, T, -1)[:, :, : model.config.vocab_size]
+        ctx.mark_non_differentiable(logits)
+        return logits, bufs.loss.view(())
+
+    @staticmethod
+    def backward(ctx, _grad_logits, grad_loss):
+        ctx.model._backward_plan(ctx.bufs, ctx.idx, ctx.targets, grad_loss)
+        return None, None, None, None
+
+
+class GPT(nn.Module):
+    def __init__(self, config: GPTConfig):
+        super().__init__()
+        assert config.vocab_size is not None and config.block_size is not None
+        assert config.n_embd // config.n_head == 64, "the sm_100a attention kernels are specialised for head size 64"
+        self.config = config
+        self.transformer = nn.ModuleDict(dict(
+            wte=nn.Embedding(config.vocab_size, config.n_embd),
+            wpe=nn.Embedding(config.block_size, config.n_embd),
+            drop=nn.Dropout(config.dropout),
+            h=nn.ModuleList([Block(config) for _ in range(config.n_layer)]),
+            ln_f=LayerNorm(config.n_embd, bias=config.bias),
+        ))
+        self.lm_head = nn.Linear(config.n_embd, config.vocab_size, bias=False)
+        self.transformer.wte.weight = self.lm_head.weight  # weight tying (model.py:138)
+        self.apply(self._init_weights)
+        for pn, p in self.named_parameters():
+            if pn.endswith("c_proj.weight"):
+                torch.nn.init.normal_(p, mean=0.0, std=0.02 / math.sqrt(2 * config.n_layer))
+        self._arena = None
+        self._bufs = {}
+        self._shadow_fresh = False
+        self._pending_clip = None
+        self.require_backward_grad_sync = True
+        self._grad_sync = None  # set by ddp.DDP
+        self._flatten()
+        print("number of parameters: %.2fM" % (self.get_num_params() / 1e6,))
+
+    # ------------------------------------------------------------------------------------------------------
+    # parameter arena
+    # ------------------------------------------------------------------------------------------------------
+    def _ordered_params(self):
+        """decay (dim >= 2) tensors first in layer order, then the 1-D tensors; each start 16-byte aligned."""
+        named = list(self.named_parameters())
+        return [(n, p) for n, p in named if p.dim() >= 2] + [(n, p) for n, p in named if p.dim() < 2]
+
+    def _flatten(self):
+        params = self._ordered_params()
+        device = params[0][1].device
+        offs, total = [], 0
+        for _, p in params:
+            offs.append(total)
+            total += _round_up(p.numel(), 8)
+        n_decay = sum(_round_up(p.numel(), 8) for _, p in params if p.dim() >= 2)
+        flat = torch.zeros(total, device=device, dtype=torch.float32)
+        for (_, p), o in zip(params, offs):
+            flat[o:o + p.numel()].copy_(p.data.reshape(-1).to(torch.float32))
+            p.data = flat[o:o + p.numel()].view(p.shape)
+            p.grad = None
+        self._arena = {
+            "flat": flat, "offs": offs, "names": [n for n, _ in params], "params": [p for _, p in params],
+            "n_decay": n_decay, "total": total, "grad": None, "shadow": None,
+        }
+        self._bufs = {}
+        self._shadow_fresh = False
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        if self._arena is not None:
+            self._flatten()  # .to()/.cuda()/.float() re-point parameters: rebuild the arena on the new device
+        return out
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=False)
+        self._shadow_fresh = False
+        return out
+
+    def _view(self, which, name):
+        a = self._arena
+        i = a["names"].index(name)
+        p = a["params"][i]
+        return a[which][a["offs"][i]:a["offs"][i] + p.numel()].view(p.shape)
+
+    def _ensure_device_state(self):
+        a = self._arena
+        if not a["flat"].is_cuda:
+            raise _C.AbcgptError("GPT: parameters are not on a CUDA device (there is no CPU path; call model.to('cuda'))")
+        if a["shadow"] is None:
+            a["shadow"] = torch.empty(a["total"], device=a["flat"].device, dtype=torch.bfloat16)
+            self._shadow_fresh = False
+        if a["grad"] is None:
+            a["grad"] = torch.zeros(a["total"], device=a["flat"].device, dtype=torch.float32)
+        if not self._shadow_fresh:
+            ops.cast_bf16(a["flat"], a["shadow"])
+            self._shadow_fresh = True
+
+    def _layer_tensors(self):
+        """Per-layer (fp32 master, bf16 shadow, grad) views, cached per arena."""
+        a = self._arena
+        if "layers" in a and a["layers_for"] == (a["shadow"].data_ptr(), a["grad"].data_ptr()):
+            return a["layers"]
+        cfg = self.config
+
+        def tri(name, need_shadow=True):
+            if name not in a["names"]:
+                return None
+            return (self._view("flat", name), self._view("shadow", name) if need_shadow else None, self._view("grad", name))
+
+        layers = []
+        for i in range(cfg.n_layer):
+            p = f"transformer.h.{i}."
+            layers.append({k: tri(p + k, need_shadow=k.endswith("weight") and "ln_" not in k) for k in (
+                "ln_1.weight", "ln_1.bias", "attn.c_attn.weight", "attn.c_attn.bias", "attn.c_proj.weight",
+                "attn.c_proj.bias", "ln_2.weight", "ln_2.bias", "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight",
+                "mlp.c_proj.bias")})
+        wte_name = "lm_head.weight" if "lm_head.weight" in a["names"] else "transformer.wte.weight"
+        top = {"wte": tri(wte_name), "wpe": tri("transformer.wpe.weight", need_shadow=False),
+               "ln_f.weight": tri("transformer.ln_f.weight", False), "ln_f.bias": tri("transformer.ln_f.bias", False)}
+        a["layers"], a["top"] = layers, top
+        a["layers_for"] = (a["shadow"].data_ptr(), a["grad"].data_ptr())
+        return layers
+
+    # ------------------------------------------------------------------------------------------------------
+    # launch plans
+    # ------------------------------------------------------------------------------------------------------
+    def _buffers(self, B, T, keep):
+        key = (B, T, keep)
+        if key not in self._bufs:
+            self._bufs[key] = _Buffers(self.config, B, T, self._arena["flat"].device, keep)
+        return self._bufs[key]
+
+    def _forward_plan(self, idx, targets, keep_activations):
+        cfg = self.config
+        if self.training and cfg.dropout != 0.0:
+            raise NotImplementedError("dropout > 0 is not implemented in the sm_100a kernels yet (parity and "
+                                      "benchmark runs use dropout=0.0 like the reference's bench.py)")
+        if not idx.is_cuda:
+            raise _C.AbcgptError("GPT.forward: idx must be a CUDA tensor (there is no CPU path)")
+        self._ensure_device_state()
+        layers = self._layer_tensors()
+        top = self._arena["top"]
+        B, T = idx.shape
+        assert T <= cfg.block_size, f"Cannot forward sequence of length {T}, block size is only {cfg.block_size}"
+        bufs = self._buffers(B, T, keep_activations)
+        C, H, V = cfg.n_embd, cfg.n_head, cfg.vocab_size
+        idx = idx.contiguous()
+        ops.embed_fwd(idx, top["wte"][0], top["wpe"][0], bufs.x[0], T)
+        for li, lw in enumerate(layers):
+            k = li if keep_activations else 0
+            x_in, x_out = bufs.x[k], bufs.x[k + 1] if keep_activations else bufs.x[0]
+            st = bufs.stat[k]
+            b = lambda name: None if lw[name] is None else lw[name][0]  # noqa: E731
+            ops.layernorm_fwd(x_in, lw["ln_1.weight"][0], b("ln_1.bias"), bufs.ln1[k], st[0], st[1])
+            ops.gemm(bufs.ln1[k], lw["attn.c_attn.weight"][1], epilogue=ops.EPI_BF16, out=bufs.qkv[k], bias=b("attn.c_attn.bias"))
+            ops.attn_fwd(bufs.qkv[k], bufs.att[k], bufs.lse[k], B, T, H)
+            ops.gemm(bufs.att[k], lw["attn.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=bufs.xmid[k], aux=x_in,
+                     bias=b("attn.c_proj.bias"))
+            ops.layernorm_fwd(bufs.xmid[k], lw["ln_2.weight"][0], b("ln_2.bias"), bufs.ln2[k], st[2], st[3])
+            ops.gemm(bufs.ln2[k], lw["mlp.c_fc.weight"][1], epilogue=ops.EPI_GELU, out=bufs.h[k], out2=bufs.g[k],
+                     bias=b("mlp.c_fc.bias"))
+            ops.gemm(bufs.g[k], lw["mlp.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=x_out, aux=bufs.xmid[k],
+                     bias=b("mlp.c_proj.bias"))
+        x_last = bufs.x[cfg.n_layer] if keep_activations else bufs.x[0]
+        lnf_b = None if top["ln_f.bias"] is None else top["ln_f.bias"][0]
+        ops.layernorm_fwd(x_last, top["ln_f.weight"][0], lnf_b, bufs.lnf, bufs.statf[0], bufs.statf[1])
+        wte_bf16 = top["wte"][1]
+        if targets is not None:
+            ops.gemm(bufs.lnf, wte_bf16, N=bufs.Vpad, epilogue=ops.EPI_BF16, out=bufs.logits)
+            ops.ce_fwd(bufs.logits, targets.contiguous().view(-1), bufs.row_loss, bufs.sum_count, bufs.loss, V)
+        else:  # last position only (model.py:190): strided A operand, no gather copy
+            a = bufs.lnf.view(B, T * C)[:, (T - 1) * C:]
+            ops.gemm(a, wte_bf16, M=B, N=bufs.Vpad, K=C, epilogue=ops.EPI_BF16, out=bufs.last_logits)
+        return bufs
+
+    def _backward_plan(self, bufs, idx, targets, grad_loss):
+        cfg = self.config
+        a = self._arena
+        layers = self._layer_tensors()
+        top = a["top"]
+        B, T, M = bufs.B, bufs.T, bufs.M
+        C, H, V = cfg.n_embd, cfg.n_head, cfg.vocab_size
+        params = a["params"]
+        if params[0].grad is None:  # first micro-step after zero_grad(set_to_none=True): start from zero
+            a["grad"].zero_()
+            for p, o in zip(params, a["offs"]):
+                p.grad = a["grad"][o:o + p.numel()].view(p.shape)
+        gl = grad_loss.to(torch.float32).reshape(1).contiguous()
+        tflat = targets.contiguous().view(-1)
+        ops.ce_bwd(bufs.logits, tflat, bufs.sum_count, gl, bufs.dlogits, V)
+        wte, wte_bf16, dwte = top["wte"]
+        # lm_head: dW[V,C] += dlogits^T lnf ; d(lnf) = dlogits W
+        ops.gemm(bufs.dlogits, bufs.lnf, a_mn=True, b_mn=True, M=V, N=C, K=M, epilogue=ops.EPI_F32_RED, out=dwte)
+        ops.gemm(bufs.dlogits, wte_bf16, b_mn=True, M=M, N=C, K=V, epilogue=ops.EPI_BF16, out=bufs.dln)
+        dx, dx_other = bufs.dx[0], bufs.dx[1]
+        gw = lambda t: None if t is None else t[2]  # noqa: E731
+        ops.layernorm_bwd(bufs.dln, bufs.x[cfg.n_layer], top["ln_f.weight"][0], bufs.statf[0], bufs.statf[1], None, dx,
+                          bufs.dxb, top["ln_f.weight"][2], gw(top["ln_f.bias"]))
+        for li in range(cfg.n_layer - 1, -1, -1):
+            lw = layers[li]
+            st = bufs.stat[li]
+            # ---- MLP: x_out = xmid + c_proj(gelu(c_fc(ln_2(xmid))))
+            ops.gemm(bufs.dxb, bufs.g[li], a_mn=True, b_mn=True, epilogue=ops.EPI_F32_RED, out=lw["mlp.c_proj.weight"][2])
+            if lw["mlp.c_proj.bias"] is not None:
+                ops.colsum_bf16(bufs.dxb, lw["mlp.c_proj.bias"][2])
+            ops.gemm(bufs.dxb, lw["mlp.c_proj.weight"][1], b_mn=True, epilogue=ops.EPI_DGELU, out=bufs.dh, aux=bufs.h[li])
+            ops.gemm(bufs.dh, bufs.ln2[li], a_mn=True, b_mn=True, epilogue=ops.EPI_F32_RED, out=lw["mlp.c_fc.weight"][2])
+            if lw["mlp.c_fc.bias"] is not None:
+                ops.colsum_bf16(bufs.dh, lw["mlp.c_fc.bias"][2])
+            ops.gemm(bufs.dh, lw["mlp.c_fc.weight"][1], b_mn=True, epilogue=ops.EPI_BF16, out=bufs.dln)
+            ops.layernorm_bwd(bufs.dln, bufs.xmid[li], lw["ln_2.weight"][0], st[2], st[3], dx, dx_other, bufs.dxb,
+                              lw["ln_2.weight"][2], gw(lw["ln_2.bias"]))
+            dx, dx_other = dx_other, dx
+            # ---- attention: xmid = x_in + c_proj(attn(c_attn(ln_1(x_in))))
+            ops.gemm(bufs.dxb, bufs.att[li], a_mn=True, b_mn=True, epilogue=ops.EPI_F32_RED, out=lw["attn.c_proj.weight"][2])
+            if lw["attn.c_proj.bias"] is not None:
+                ops.colsum_bf16(bufs.dxb, lw["attn.c_proj.bias"][2])
+            ops.gemm(bufs.dxb, lw["attn.c_proj.weight"][1], b_mn=True, epilogue=ops.EPI_BF16, out=bufs.datt)
+            ops.attn_bwd(bufs.qkv[li], bufs.att[li], bufs.datt, bufs.lse[li], bufs.delta, bufs.dqkv, B, T, H)
+            ops.gemm(bufs.dqkv, bufs.ln1[li], a_mn=True, b_mn=True, epilogue=ops.EPI_F32_RED, out=lw["attn.c_attn.weight"][2])
+            if lw["attn.c_attn.bias"] is not None:
+                ops.colsum_bf16(bufs.dqkv, lw["attn.c_attn.bias"][2])
+            ops.gemm(bufs.dqkv, lw["attn.c_attn.weight"][1], b_mn=True, epilogue=ops.EPI_BF16, out=bufs.dln)
+            ops.layernorm_bwd(bufs.dln, bufs.x[li], lw["ln_1.weight"][0], st[0], st[1], dx, dx_other, bufs.dxb,
+                              lw["ln_1.weight"][2], gw(lw["ln_1.bias"]))
+            dx, dx_other = dx_other, dx
+            if self._grad_sync is not None and self.require_backward_grad_sync:
+                self._grad_sync.layer_done(li)
+        ops.embed_bwd(idx.contiguous().view(-1), dx, dwte, top["wpe"][2], T)
+        if self._grad_sync is not None and self.require_backward_grad_sync:
+            self._grad_sync.backward_done()
+
+    # ------------------------------------------------------------------------------------------------------
+    # reference call surface
+    # ------------------------------------------------------------------------------------------------------
+    def get_num_params(self, non_embedding=True):
+        n_params = sum(p.numel() for p in self.parameters())
+        if non_embedding:
+            n_params -= self.transformer.wpe.weight.numel()
+        return n_params
+
+    def _init_weights(self, module):
+        if isinstance(module, nn.Linear):
+            torch.nn.init.normal_(module.weight, mean=0.0, std=0.02)
+            if module.bias is not None:
+                torch.nn.init.zeros_(module.bias)
+        elif isinstance(module, nn.Embedding):
+            torch.nn.init.normal_(module.weight, mean=0.0, std=0.02)
+
+    def forward(self, idx, targets=None):
+        B, T = idx.size()
+        if targets is not None and torch.is_grad_enabled() and self._arena["params"][0].requires_grad:
+            anchor = self._anchor_tensor(idx.device)
+            logits, loss = _GPTStep.apply(anchor, self, idx, targets)
+            return logits, loss
+        with torch.no_grad():
+            bufs = self._forward_plan(idx, targets, keep_activations=False)
+        V = self.config.vocab_size
+        if targets is not None:
+            return bufs.logits.view(B, T, -1)[:, :, :V], bufs.loss.view(())
+        return bufs.last_logits[:, :V].unsqueeze(1), None
+
+    def _anchor_tensor(self, device):
+        t = getattr(self, "_anchor", None)
+        if t is None or t.device != device:
+            t = torch.zeros(1, device=device, requires_grad=True)
+            object.__setattr__(self, "_anchor", t)
+        return t
+
+    def crop_block_size(self, block_size):
+        assert block_size <= self.config.block_size
+        self.config.block_size = block_size
+        self.transformer.wpe.weight = nn.Parameter(self.transformer.wpe.weight[:block_size].detach().clone())
+        self._flatten()
+
+    def configure_optimizers(self, weight_decay, learning_rate, betas, device_type):
+        param_dict = {pn: p for pn, p in self.named_parameters() if p.requires_grad}
+        decay_params = [p for n, p in param_dict.items() if p.dim() >= 2]
+        nodecay_params = [p for n, p in param_dict.items() if p.dim() < 2]
+        optim_groups = [
+            {"params": decay_params, "weight_decay": weight_decay},
+            {"params": nodecay_params, "weight_decay": 0.0},
+        ]
+        print(f"num decayed parameter tensors: {len(decay_params)}, with {sum(p.numel() for p in decay_params):,} parameters")
+        print(f"num non-decayed parameter tensors: {len(nodecay_params)}, with {sum(p.numel() for p in nodecay_params):,} parameters")
+        optimizer = FusedAdamW(optim_groups, lr=learning_rate, betas=betas, model=self)
+        print("using fused AdamW: True (sm_100a arena kernel)")
+        return optimizer
+
+    def clip_grad_norm_(self, max_norm):
+        """Fused counterpart of torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) (train.py:352): one
+        sum-of-squares launch now, the scaling itself is folded into the next optimizer.step().  Returns the total
+        gradient norm as a 0-d device tensor (no host sync)."""
+        a = self._arena
+        if a["grad"] is None or a["params"][0].grad is None:
+            raise RuntimeError("clip_grad_norm_: no gradients (call loss.backward() first)")
+        if self._grad_sync is not None:
+            self._grad_sync.wait()
+        ss = a.setdefault("sumsq", torch.zeros(1, device=a["flat"].device, dtype=torch.float32))
+        ss.zero_()
+        ops.sumsq(a["grad"], ss)
+        self._pending_clip = (ss, float(max_norm))
+        return ss.sqrt().view(())
+
+    def estimate_mfu(self, fwdbwd_per_iter, dt, flops_promised=312e12):
+        """Same formula as the reference (model.py:289-303); `flops_promised` defaults to the reference's A100
+        constant so numbers are comparable, pass 2.25e15 for B200 dense bf16."""
+        N = self.get_num_params()
+        cfg = self.config
+        L, H, Q, T = cfg.n_layer, cfg.n_head, cfg.n_embd // cfg.n_head, cfg.block_size
+        flops_per_token = 6 * N + 12 * L * H * Q * T
+        flops_per_iter = flops_per_token * T * fwdbwd_per_iter
+        return flops_per_iter * (1.0 / dt) / flops_promised
+
+    @torch.no_grad()
+    def generate(self, idx, max_new_tokens, temperature=1.0, top_k=None):
+        """Reference semantics (model.py:305-330): context cropped to block_size, last-position logits, temperature,
+        optional top-k, sample, append.  top_k == 1 (greedy) uses the fused argmax head and a pre-allocated token
+        buffer; other settings sample from the [B, V] last-position logits."""
+        B, T0 = idx.shape
+        V = self.config.vocab_size
+        out = torch.empty(B, T0 + max_new_tokens, device=idx.device, dtype=torch.int64)
+        out[:, :T0] = idx
+        for i in range(max_new_tokens):
+            t = T0 + i
+            lo = max(0, t - self.config.block_size)
+            cond = out[:, lo:t].contiguous()
+            bufs = self._forward_plan(cond, None, keep_activations=False)
+            if top_k is not None and min(top_k, V) == 1:
+                ops.argmax(bufs.last_logits, V, out[:, t:], out_stride=out.stride(0))
+                continue
+            logits = bufs.last_logits[:, :V].float() / temperature
+            if top_k is not None:
+                v, _ = torch.topk(logits, min(top_k, V))
+                logits[logits < v[:, [-1]]] = -float("Inf")
+            probs = torch.softmax(logits, dim=-1)
+            out[:, t] = torch.multinomial(probs, num_samples=1).view(-1)
+        return out

@@ -11,6 +11,31 @@ from . import _C
 from ._C import EPI_BF16, EPI_DGELU, EPI_F32, EPI_F32_RED, EPI_GELU, EPI_RESID  # noqa: F401
 
 
+LAUNCHES = 0      # kernels of libabcgpt.so enqueued so far (bench.py reports the delta over its timed region)
+_PROFILE = None   # optional list collecting (name, meta, start_event, end_event) per C-ABI call
+
+
+def set_profile(sink):
+    """sink: None or a list; when set, every call is bracketed by CUDA events on the launching stream."""
+    global _PROFILE
+    _PROFILE = sink
+
+
+def _call(name, nkernels, meta, fn, *args):
+    global LAUNCHES
+    LAUNCHES += nkernels
+    if _PROFILE is None:
+        rc = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _PROFILE.append((name, meta, e0, e1))
+    if rc != 0:
+        _C.check(rc, name)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -52,10 +77,9 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_B
     ldaux = _rowmajor_ld(aux, "gemm aux") if aux is not None else 0
     if bias is not None:
         _chk(bias, torch.float32, "gemm bias")
-    rc = _C.lib().abcgpt_gemm_bf16(a.data_ptr(), int(a_mn), lda, b.data_ptr(), int(b_mn), ldb, M, N, K, epilogue,
-                                  out.data_ptr(), ldc, _ptr(out2), ldc2, _ptr(aux), ldaux, _ptr(bias), tile_n, splits,
-                                  _stream())
-    _C.check(rc, "abcgpt_gemm_bf16")
+    _call("gemm", 1, (M, N, K, int(a_mn), int(b_mn), epilogue), _C.lib().abcgpt_gemm_bf16, a.data_ptr(), int(a_mn), lda,
+          b.data_ptr(), int(b_mn), ldb, M, N, K, epilogue, out.data_ptr(), ldc, _ptr(out2), ldc2, _ptr(aux), ldaux,
+          _ptr(bias), tile_n, splits, _stream())
     return out
 
 
@@ -63,41 +87,41 @@ def embed_fwd(idx, wte, wpe, x, T):
     _chk(idx, torch.int64, "embed idx")
     M = idx.numel()
     V, C = wte.shape
-    _C.check(_C.lib().abcgpt_embed_fwd(idx.data_ptr(), wte.data_ptr(), wpe.data_ptr(), x.data_ptr(), M, T, C, V, _stream()),
-             "abcgpt_embed_fwd")
+    _call("embed_fwd", 1, (M, C), _C.lib().abcgpt_embed_fwd, idx.data_ptr(), wte.data_ptr(), wpe.data_ptr(), x.data_ptr(),
+          M, T, C, V, _stream())
     return x
 
 
 def embed_bwd(idx, dx, dwte, dwpe, T):
     M = idx.numel()
     V, C = dwte.shape
-    _C.check(_C.lib().abcgpt_embed_bwd(idx.data_ptr(), dx.data_ptr(), dwte.data_ptr(), dwpe.data_ptr(), M, T, C, V, _stream()),
-             "abcgpt_embed_bwd")
+    _call("embed_bwd", 2, (M, C), _C.lib().abcgpt_embed_bwd, idx.data_ptr(), dx.data_ptr(), dwte.data_ptr(),
+          dwpe.data_ptr(), M, T, C, V, _stream())
 
 
 def layernorm_fwd(x, weight, bias, y_bf16, mean, rstd, y_f32=None):
     _chk(x, torch.float32, "layernorm x")
     M, C = x.shape
-    _C.check(_C.lib().abcgpt_layernorm_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(y_bf16), _ptr(y_f32),
-                                          _ptr(mean), _ptr(rstd), M, C, _stream()), "abcgpt_layernorm_fwd")
+    _call("layernorm_fwd", 1, (M, C), _C.lib().abcgpt_layernorm_fwd, x.data_ptr(), weight.data_ptr(), _ptr(bias),
+          _ptr(y_bf16), _ptr(y_f32), _ptr(mean), _ptr(rstd), M, C, _stream())
 
 
 def layernorm_bwd(dy_bf16, x, weight, mean, rstd, dresid_in, dx_out, dx_bf16, dweight, dbias):
     M, C = x.shape
-    _C.check(_C.lib().abcgpt_layernorm_bwd(dy_bf16.data_ptr(), x.data_ptr(), weight.data_ptr(), mean.data_ptr(),
-                                          rstd.data_ptr(), _ptr(dresid_in), dx_out.data_ptr(), _ptr(dx_bf16),
-                                          _ptr(dweight), _ptr(dbias), M, C, _stream()), "abcgpt_layernorm_bwd")
+    _call("layernorm_bwd", 1, (M, C), _C.lib().abcgpt_layernorm_bwd, dy_bf16.data_ptr(), x.data_ptr(), weight.data_ptr(),
+          mean.data_ptr(), rstd.data_ptr(), _ptr(dresid_in), dx_out.data_ptr(), _ptr(dx_bf16), _ptr(dweight),
+          _ptr(dbias), M, C, _stream())
 
 
 def attn_fwd(qkv, out, lse, B, T, H):
     _chk(qkv, torch.bfloat16, "attn qkv")
-    _C.check(_C.lib().abcgpt_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, H, _stream()),
-             "abcgpt_attn_fwd")
+    _call("attn_fwd", 1, (B, T, H), _C.lib().abcgpt_attn_fwd, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, H,
+          _stream())
 
 
 def attn_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H):
-    _C.check(_C.lib().abcgpt_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
-                                     dqkv.data_ptr(), B, T, H, _stream()), "abcgpt_attn_bwd")
+    _call("attn_bwd", 3, (B, T, H), _C.lib().abcgpt_attn_bwd, qkv.data_ptr(), out.data_ptr(), dout.data_ptr(),
+          lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, T, H, _stream())
 
 
 def ce_fwd(logits, targets, row_loss, sum_count, loss, V):
@@ -105,32 +129,36 @@ def ce_fwd(logits, targets, row_loss, sum_count, loss, V):
     _chk(targets, torch.int64, "ce targets")
     M, ldl = logits.shape[0], logits.stride(0)
     L = _C.lib()
-    _C.check(L.abcgpt_ce_fwd(logits.data_ptr(), ldl, targets.data_ptr(), row_loss.data_ptr(), M, V, _stream()),
-             "abcgpt_ce_fwd")
-    _C.check(L.abcgpt_ce_finalize(row_loss.data_ptr(), targets.data_ptr(), M, sum_count.data_ptr(), _ptr(loss), _stream()),
-             "abcgpt_ce_finalize")
+    _call("ce_fwd", 1, (M, V), L.abcgpt_ce_fwd, logits.data_ptr(), ldl, targets.data_ptr(), row_loss.data_ptr(), M, V,
+          _stream())
+    _call("ce_finalize", 1, (M,), L.abcgpt_ce_finalize, row_loss.data_ptr(), targets.data_ptr(), M, sum_count.data_ptr(),
+          _ptr(loss), _stream())
 
 
 def ce_bwd(logits, targets, sum_count, grad_loss, dlogits, V):
     M, ldl = logits.shape[0], logits.stride(0)
-    _C.check(_C.lib().abcgpt_ce_bwd(logits.data_ptr(), ldl, targets.data_ptr(), sum_count.data_ptr(), grad_loss.data_ptr(),
-                                   dlogits.data_ptr(), M, V, _stream()), "abcgpt_ce_bwd")
+    _call("ce_bwd", 1, (M, V), _C.lib().abcgpt_ce_bwd, logits.data_ptr(), ldl, targets.data_ptr(), sum_count.data_ptr(),
+          grad_loss.data_ptr(), dlogits.data_ptr(), M, V, _stream())
 
 
 def sumsq(g, out):
-    _C.check(_C.lib().abcgpt_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "abcgpt_sumsq")
+    _call("sumsq", 1, (g.numel(),), _C.lib().abcgpt_sumsq, g.data_ptr(), g.numel(), out.data_ptr(), _stream())
 
 
 def adamw(p, g, m, v, shadow, *, lr, beta1, beta2, eps, weight_decay, step, sumsq=None, max_norm=0.0):
-    _C.check(_C.lib().abcgpt_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), p.numel(),
-                                  lr, beta1, beta2, eps, weight_decay, step, _ptr(sumsq), max_norm, _stream()),
-             "abcgpt_adamw")
+    _call("adamw", 1, (p.numel(),), _C.lib().abcgpt_adamw, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+          _ptr(shadow), p.numel(), lr, beta1, beta2, eps, weight_decay, step, _ptr(sumsq), max_norm, _stream())
 
 
 def cast_bf16(x, y):
-    _C.check(_C.lib().abcgpt_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "abcgpt_cast_f32_to_bf16")
+    _call("cast_bf16", 1, (x.numel(),), _C.lib().abcgpt_cast_f32_to_bf16, x.data_ptr(), y.data_ptr(), x.numel(), _stream())
 
 
 def argmax(logits, V, out, out_stride=1):
     B, ldl = logits.shape[0], logits.stride(0)
-    _C.check(_C.lib().abcgpt_argmax(logits.data_ptr(), ldl, V, out.data_ptr(), out_stride, B, _stream()), "abcgpt_argmax")
+    _call("argmax", 1, (B, V), _C.lib().abcgpt_argmax, logits.data_ptr(), ldl, V, out.data_ptr(), out_stride, B, _stream())
+
+
+def colsum_bf16(dy, out):
+    M, N = dy.shape
+    _call("colsum_bf16", 1, (M, N), _C.lib().abcgpt_colsum_bf16, dy.data_ptr(), dy.stride(0), M, N, out.data_ptr(), _stream())

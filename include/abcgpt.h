@@ -112,6 +112,9 @@ int abcgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16
 /* y(bf16) = x(fp32), elementwise; used to (re)build the bf16 weight shadow after load_state_dict */
 int abcgpt_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
 
+/* out[n] += sum_m dy[m,n]: bias gradient of an nn.Linear with bias=True (dy bf16 [M, ld], out fp32 [N]) */
+int abcgpt_colsum_bf16(const void* dy, int64_t ld, int M, int N, float* out, void* stream);
+
 /*
  * Greedy / top-k sampling head for generate()                                    model.py:316-328
  * logits bf16 [B, ldl] (last position only); writes the argmax token id (int64) per row into out[b*out_stride].

@@ -1,0 +1,38 @@
+"""Per-kernel parity on the GPU through the C ABI (ctypes -> libabcgpt.so), each kernel against a plain fp32
+PyTorch statement of the same op.  The case definitions live in tools/gpu_probe.py (also used for timing)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tools import gpu_probe  # noqa: E402
+
+FAST_CASES = [
+    "gemm_nt_small_bn128", "gemm_nt_small_bn256", "gemm_nn_small_bn128", "gemm_nn_small_bn256",
+    "gemm_tn_small_bn128", "gemm_tn_small_bn256", "gemm_nt_k256_bn256", "gemm_nt_ragged", "gemm_nt_f32",
+    "gemm_gelu", "gemm_resid", "gemm_dgelu", "gemm_wgrad_red",
+    "attn_t32", "attn_t128", "attn_t200", "attn_t256", "attn_t1024",
+    "ln_384", "ln_768", "ln_768_bias", "ln_1000", "ce_95", "ce_50304", "adamw", "embed", "embed_bigv",
+]
+
+
+@pytest.mark.parametrize("name", FAST_CASES)
+def test_kernel_case(name, cuda_device):
+    res = gpu_probe.build_cases()[name]()
+    assert res["ok"], res
+
+
+def test_full_size_gemm_shapes(cuda_device):
+    """BASELINE cfg3 shapes (M = 32*1024): bf16 rounding-level agreement with an fp32 matmul."""
+    cases = gpu_probe.build_cases()
+    for name in ("gemm_perf_c_attn", "gemm_perf_mlp_proj_resid", "gemm_perf_dgrad_proj_dgelu", "gemm_perf_wgrad_fc",
+                 "gemm_perf_lm_head"):
+        res = cases[name]()
+        assert res["ok"], res
+
+
+def test_missing_cuda_tensor_is_loud(cuda_device):
+    import torch
+    from ai_music_generation_b200 import _C, ops
+    with pytest.raises(_C.AbcgptError):
+        ops.gemm(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(128, 64, dtype=torch.bfloat16),
+                 out=torch.zeros(128, 128, dtype=torch.bfloat16))
