@@ -145,6 +145,9 @@ def _attention(qkv, n_head, bf16):
     q = q.view(B, T, n_head, hs).transpose(1, 2)
     k = k.view(B, T, n_head, hs).transpose(1, 2)
     v = v.view(B, T, n_head, hs).transpose(1, 2)
+    if not bf16:  # same call the reference makes (model.py:64); the explicit form below is its definition (:67-71)
+        y = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=True)
+        return y.transpose(1, 2).contiguous().view(B, T, C)
     att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(hs))
     mask = torch.ones(T, T, dtype=torch.bool).tril()
     att = att.masked_fill(~mask, float("-inf"))
