@@ -4,6 +4,7 @@
 #include "kernels.h"
 
 using namespace abcgpt;
+namespace abcgpt { extern unsigned long long* g_gemm_stats; }
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
 
@@ -73,6 +74,12 @@ int abcgpt_colsum_bf16(const void* dy, int64_t ld, int M, int N, float* out, voi
 }
 int abcgpt_argmax(const void* logits, int64_t ldl, int V, int64_t* out, int64_t out_stride, int B, void* stream) {
   return argmax_rows(logits, ldl, V, out, out_stride, B, S(stream));
+}
+
+/* debug: device pointer to 8 uint64 cycle counters filled by subsequent GEMM launches (NULL disables) */
+int abcgpt_debug_gemm_stats(void* device_counters) {
+  abcgpt::g_gemm_stats = reinterpret_cast<unsigned long long*>(device_counters);
+  return 0;
 }
 
 }  // extern "C"

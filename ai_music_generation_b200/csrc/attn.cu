@@ -51,6 +51,140 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t slab_addr, int k16) {
   return ptx::umma_smem_desc(slab_addr + k16 * 2048, 8192, 1024);
 }
 
+
+__device__ __forceinline__ float2 f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+
+// Per-chunk mask classes (a chunk = 32 consecutive score columns seen by one warp = 32 consecutive rows).  Row and
+// column ranges are both 32-aligned, so a chunk is either entirely visible, entirely masked, or the diagonal one.
+constexpr int kFull = 0, kDiag = 1, kMasked = 2;
+
+// forward pass 1: row max of one chunk
+template <int MODE>
+__device__ __forceinline__ float fwd_chunk_max(uint32_t taddr, int lane) {
+  if (MODE == kMasked) return -1e30f;
+  uint32_t v[32];
+  ptx::tmem_ld32(taddr, v);
+  ptx::tmem_ld_wait();
+  float m0 = -1e30f, m1 = -1e30f, m2 = -1e30f, m3 = -1e30f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float a = __uint_as_float(v[i]), b = __uint_as_float(v[i + 1]), c = __uint_as_float(v[i + 2]), d = __uint_as_float(v[i + 3]);
+    if (MODE == kDiag) {
+      a = (i <= lane) ? a : -1e30f;
+      b = (i + 1 <= lane) ? b : -1e30f;
+      c = (i + 2 <= lane) ? c : -1e30f;
+      d = (i + 3 <= lane) ? d : -1e30f;
+    }
+    m0 = fmaxf(m0, a); m1 = fmaxf(m1, b); m2 = fmaxf(m2, c); m3 = fmaxf(m3, d);
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// forward pass 2: p = 2^(s*sl2 - m), bf16 P into the swizzled slab, returns the fp32 row-sum contribution
+template <int MODE>
+__device__ __forceinline__ float fwd_chunk_exp(uint32_t taddr, int lane, float neg_m, uint32_t slab, int r, int c32) {
+  uint32_t pk[16];
+  if (MODE == kMasked) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    st_slab32(slab, r, c32, pk);
+    return 0.f;
+  }
+  uint32_t v[32];
+  ptx::tmem_ld32(taddr, v);
+  ptx::tmem_ld_wait();
+  const float2 sl = make_float2(kSl2, kSl2), nm = make_float2(neg_m, neg_m);
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float2 t0 = __ffma2_rn(f2(v[2 * i], v[2 * i + 1]), sl, nm);
+    const float2 t1 = __ffma2_rn(f2(v[2 * i + 2], v[2 * i + 3]), sl, nm);
+    float2 p0 = make_float2(ex2(t0.x), ex2(t0.y));
+    float2 p1 = make_float2(ex2(t1.x), ex2(t1.y));
+    if (MODE == kDiag) {
+      p0.x = (2 * i <= lane) ? p0.x : 0.f;
+      p0.y = (2 * i + 1 <= lane) ? p0.y : 0.f;
+      p1.x = (2 * i + 2 <= lane) ? p1.x : 0.f;
+      p1.y = (2 * i + 3 <= lane) ? p1.y : 0.f;
+    }
+    acc0 = __fadd2_rn(acc0, p0);
+    acc1 = __fadd2_rn(acc1, p1);
+    pk[i] = ptx::pack_bf16x2(p0.x, p0.y);
+    pk[i + 1] = ptx::pack_bf16x2(p1.x, p1.y);
+  }
+  st_slab32(slab, r, c32, pk);
+  return (acc0.x + acc0.y) + (acc1.x + acc1.y);
+}
+
+// backward (dQ kernel): dS = P * (dP*scale - delta*scale) for one chunk; row statistics are per thread
+template <int MODE>
+__device__ __forceinline__ void dq_chunk(uint32_t taddr_s, uint32_t taddr_dp, int lane, float neg_lse2, float neg_delta8,
+                                         uint32_t* pk) {
+  if (MODE == kMasked) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    return;
+  }
+  uint32_t s[32], dp[32];
+  ptx::tmem_ld32(taddr_s, s);
+  ptx::tmem_ld32(taddr_dp, dp);
+  ptx::tmem_ld_wait();
+  const float2 sl = make_float2(kSl2, kSl2), nl = make_float2(neg_lse2, neg_lse2);
+  const float2 sc = make_float2(kScale, kScale), nd = make_float2(neg_delta8, neg_delta8);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 t = __ffma2_rn(f2(s[2 * i], s[2 * i + 1]), sl, nl);
+    const float2 p = make_float2(ex2(t.x), ex2(t.y));
+    const float2 u = __ffma2_rn(f2(dp[2 * i], dp[2 * i + 1]), sc, nd);
+    float2 d = __fmul2_rn(p, u);
+    if (MODE == kDiag) {  // keep column <= row
+      d.x = (2 * i <= lane) ? d.x : 0.f;
+      d.y = (2 * i + 1 <= lane) ? d.y : 0.f;
+    }
+    pk[i] = ptx::pack_bf16x2(d.x, d.y);
+  }
+}
+
+// backward (dK/dV kernel): P^T and dS^T for one chunk; statistics are per COLUMN (query), read from shared memory.
+// MODE kDiag here is the general path: keep iff (q >= kv) && (q < T).
+template <int MODE>
+__device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, const float* st_lse2, const float* st_delta8,
+                                          int q_base, int kv_t, int T, uint32_t* pk_p, uint32_t* pk_ds) {
+  if (MODE == kMasked) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; pk_ds[i] = 0u; }
+    return;
+  }
+  uint32_t s[32], dp[32];
+  ptx::tmem_ld32(taddr_s, s);
+  ptx::tmem_ld32(taddr_dp, dp);
+  ptx::tmem_ld_wait();
+  const float2 sl = make_float2(kSl2, kSl2), sc = make_float2(kScale, kScale);
+#pragma unroll
+  for (int i4 = 0; i4 < 8; ++i4) {
+    const float4 l4 = reinterpret_cast<const float4*>(st_lse2)[i4];     // already negated: -lse*log2e
+    const float4 d4 = reinterpret_cast<const float4*>(st_delta8)[i4];   // already negated: -delta*scale
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * i4 + h;  // pair index: columns 2i, 2i+1
+      const float2 nl = h == 0 ? make_float2(l4.x, l4.y) : make_float2(l4.z, l4.w);
+      const float2 nd = h == 0 ? make_float2(d4.x, d4.y) : make_float2(d4.z, d4.w);
+      const float2 t = __ffma2_rn(f2(s[2 * i], s[2 * i + 1]), sl, nl);
+      float2 p = make_float2(ex2(t.x), ex2(t.y));
+      const float2 u = __ffma2_rn(f2(dp[2 * i], dp[2 * i + 1]), sc, nd);
+      float2 d = __fmul2_rn(p, u);
+      if (MODE == kDiag) {
+        const int q0 = q_base + 2 * i;
+        const bool k0 = (q0 >= kv_t) && (q0 < T), k1 = (q0 + 1 >= kv_t) && (q0 + 1 < T);
+        p.x = k0 ? p.x : 0.f; d.x = k0 ? d.x : 0.f;
+        p.y = k1 ? p.y : 0.f; d.y = k1 ? d.y : 0.f;
+      }
+      pk_p[i] = ptx::pack_bf16x2(p.x, p.y);
+      pk_ds[i] = ptx::pack_bf16x2(d.x, d.y);
+    }
+  }
+}
+
 // ======================================================================================================
 // forward
 // ======================================================================================================
@@ -168,38 +302,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       ptx::mbar_wait(s_full, ph, 17);
       ptx::tc_fence_after();
       float mx = -1e30f;
+      if (!diag) {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tm_S + lane_off + c * 32, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(v[i]);
-          if (!diag || (c * 32 + i) <= r) mx = fmaxf(mx, s);
-        }
+        for (int c = 0; c < 4; ++c) mx = fmaxf(mx, fwd_chunk_max<kFull>(tm_S + lane_off + c * 32, lane));
+      } else {
+#pragma unroll 1
+        for (int c = 0; c <= quarter; ++c)
+          mx = fmaxf(mx, c < quarter ? fwd_chunk_max<kFull>(tm_S + lane_off + c * 32, lane)
+                                     : fwd_chunk_max<kDiag>(tm_S + lane_off + c * 32, lane));
       }
       const float m_new = fmaxf(m, mx * kSl2);
       const float alpha = ex2(m - m_new);
       float rowsum = 0.f;
+      if (!diag) {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tm_S + lane_off + c * 32, v);
-        ptx::tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), kSl2, -m_new));
-          float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), kSl2, -m_new));
-          if (diag) {
-            if ((c * 32 + 2 * i) > r) p0 = 0.f;
-            if ((c * 32 + 2 * i + 1) > r) p1 = 0.f;
-          }
-          rowsum += p0 + p1;
-          pk[i] = ptx::pack_bf16x2(p0, p1);
+        for (int c = 0; c < 4; ++c)
+          rowsum += fwd_chunk_exp<kFull>(tm_S + lane_off + c * 32, lane, -m_new, sP + (c >> 1) * 16384, r, c & 1);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t ta = tm_S + lane_off + c * 32, slab = sP + (c >> 1) * 16384;
+          if (c < quarter) rowsum += fwd_chunk_exp<kFull>(ta, lane, -m_new, slab, r, c & 1);
+          else if (c == quarter) rowsum += fwd_chunk_exp<kDiag>(ta, lane, -m_new, slab, r, c & 1);
+          else rowsum += fwd_chunk_exp<kMasked>(ta, lane, -m_new, slab, r, c & 1);
         }
-        st_slab32(sP + (c >> 1) * 16384, r, c & 1, pk);
       }
       l = l * alpha + rowsum;
       m = m_new;
@@ -213,8 +339,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
         uint32_t v[32];
         ptx::tmem_ld32(tm_O + lane_off + c * 32, v);
         ptx::tmem_ld_wait();
+        const float2 al = make_float2(alpha, alpha);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) O[c * 32 + i] = fmaf(O[c * 32 + i], alpha, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; i += 2) {
+          const float2 o = __ffma2_rn(make_float2(O[c * 32 + i], O[c * 32 + i + 1]), al, f2(v[i], v[i + 1]));
+          O[c * 32 + i] = o.x;
+          O[c * 32 + i + 1] = o.y;
+        }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(o_empty);
@@ -370,30 +501,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     const int t = qt * 128 + r;
     const bool valid = t < T;
     const long long stat_idx = (static_cast<long long>(b) * H + h) * T + t;
-    const float lse2 = valid ? __ldg(lse + stat_idx) * kLog2e : 0.f;
-    const float dl = valid ? __ldg(delta + stat_idx) : 0.f;
+    const float neg_lse2 = valid ? -__ldg(lse + stat_idx) * kLog2e : 0.f;
+    const float neg_delta8 = valid ? -__ldg(delta + stat_idx) * kScale : 0.f;
     for (int j = 0; j < num_kv; ++j) {
       ptx::mbar_wait(s_full, j & 1, 24);
       ptx::tc_fence_after();
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t s[32], dp[32];
-        ptx::tmem_ld32(tm_S + lane_off + c * 32, s);
-        ptx::tmem_ld32(tm_dP + lane_off + c * 32, dp);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float d[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = j * 64 + c * 32 + 2 * i + e;
-            const float p = ex2(fmaf(__uint_as_float(s[2 * i + e]), kSl2, -lse2));
-            const float v = p * (__uint_as_float(dp[2 * i + e]) - dl) * kScale;
-            d[e] = (valid && col <= t) ? v : 0.f;
-          }
-          pk[c * 16 + i] = ptx::pack_bf16x2(d[0], d[1]);
-        }
+        const int c0 = j * 64 + c * 32;      // first key column of the chunk
+        const int r0 = qt * 128 + quarter * 32;  // first query row of this warp
+        const uint32_t ta_s = tm_S + lane_off + c * 32, ta_dp = tm_dP + lane_off + c * 32;
+        if (c0 + 31 <= r0) dq_chunk<kFull>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
+        else if (c0 > r0 + 31) dq_chunk<kMasked>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
+        else dq_chunk<kDiag>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
       }
       if (j > 0) ptx::mbar_wait(dq_done, (j - 1) & 1, 25);  // previous dQ MMA has finished reading dS
       st_slab32(sDS, r, 0, pk);
@@ -548,7 +669,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       {
         const int qi = q0 + (tid & 63);
         float v = 0.f;
-        if (qi < T) v = (tid < 64) ? __ldg(lse + stat_base + qi) * kLog2e : __ldg(delta + stat_base + qi);
+        if (qi < T) v = (tid < 64) ? -__ldg(lse + stat_base + qi) * kLog2e : -__ldg(delta + stat_base + qi) * kScale;
         st_lse[tid] = v;
       }
       ptx::bar_sync(1, 128);
@@ -557,26 +678,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       uint32_t pk_p[32], pk_ds[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t s[32], dp[32];
-        ptx::tmem_ld32(tm_S + lane_off + c * 32, s);
-        ptx::tmem_ld32(tm_dP + lane_off + c * 32, dp);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int cc = c * 32 + 2 * i + e;
-            const int qg = q0 + cc;
-            const float p = ex2(fmaf(__uint_as_float(s[2 * i + e]), kSl2, -st_lse[cc]));
-            const float d = p * (__uint_as_float(dp[2 * i + e]) - st_lse[64 + cc]) * kScale;
-            const bool keep = valid && qg >= kv_t && qg < T;
-            pv[e] = keep ? p : 0.f;
-            dv[e] = keep ? d : 0.f;
-          }
-          pk_p[c * 16 + i] = ptx::pack_bf16x2(pv[0], pv[1]);
-          pk_ds[c * 16 + i] = ptx::pack_bf16x2(dv[0], dv[1]);
-        }
+        const int c0 = q0 + c * 32;                 // first query column of the chunk
+        const int r0 = kt * 128 + quarter * 32;     // first key row of this warp
+        const uint32_t ta_s = tm_S + lane_off + c * 32, ta_dp = tm_dP + lane_off + c * 32;
+        const float* l2 = st_lse + c * 32;
+        const float* d8 = st_lse + 64 + c * 32;
+        if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
+        else if (c0 + 31 < r0 || c0 >= T) dkv_chunk<kMasked>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
+        else dkv_chunk<kDiag>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
       }
       if (n > 0) ptx::mbar_wait(pds_empty, (n - 1) & 1, 35);
       st_slab32(sPT, r, 0, pk_p);

@@ -18,6 +18,8 @@
 
 namespace abcgpt {
 
+unsigned long long* g_gemm_stats = nullptr;  // debug only: set through abcgpt_debug_gemm_stats
+
 namespace {
 
 constexpr int BM = 128;
@@ -36,6 +38,8 @@ struct GemmParams {
   const void* aux;
   long long ldaux;
   const float* bias;
+  unsigned long long* stats;  // optional debug counters (cycles): [0] producer empty-wait, [1] mma full-wait,
+                              // [2] mma tmem-empty wait, [3] epilogue tmem-full wait, [4] epilogue busy, [5] cta total
 };
 
 template <int BN>
@@ -164,6 +168,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
   }
 }
 
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, int tag, unsigned long long* stats, int slot,
+                                           long long& acc) {
+  if (stats == nullptr) {
+    ptx::mbar_wait(bar, parity, tag);
+  } else {
+    const long long t0 = clock64();
+    ptx::mbar_wait(bar, parity, tag);
+    acc += clock64() - t0;
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -202,6 +217,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_work = p.num_m_blk * p.num_n_blk * p.splits;
+  const long long t_start = p.stats ? clock64() : 0;
+  long long w0 = 0, w1 = 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -216,7 +233,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1, 1);
+          timed_wait(&empty[stage], phase ^ 1, 1, p.stats, 0, w0);
           ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
@@ -240,6 +257,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      if (p.stats) atomicAdd(&p.stats[0], static_cast<unsigned long long>(w0));
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -255,11 +273,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        ptx::mbar_wait(&tempty[as], aphase ^ 1, 2);
+        timed_wait(&tempty[as], aphase ^ 1, 2, p.stats, 2, w1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&full[stage], phase, 3);
+          timed_wait(&full[stage], phase, 3, p.stats, 1, w0);
           ptx::tc_fence_after();
           const uint32_t a_base = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_base = a_base + C::A_BYTES;
@@ -281,6 +299,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         ptx::umma_commit(&tfull[as]);  // accumulator complete
       }
+      if (p.stats) {
+        atomicAdd(&p.stats[1], static_cast<unsigned long long>(w0));
+        atomicAdd(&p.stats[2], static_cast<unsigned long long>(w1));
+      }
     }
     __syncwarp();
   } else {
@@ -295,7 +317,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n_blk = tile % p.num_n_blk;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      ptx::mbar_wait(&tfull[as], aphase, 4);
+      timed_wait(&tfull[as], aphase, 4, p.stats, 3, w0);
       ptx::tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
@@ -309,6 +331,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+    }
+    if (p.stats && warp == 2 && lane == 0) {
+      atomicAdd(&p.stats[3], static_cast<unsigned long long>(w0));
+      atomicAdd(&p.stats[5], static_cast<unsigned long long>(clock64() - t_start));
     }
   }
 
@@ -358,6 +384,7 @@ int dispatch_major(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CU
 int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, long long ldb, int M, int N, int K,
               int epi, void* c, long long ldc, void* c2, long long ldc2, const void* aux, long long ldaux,
               const float* bias, int bn_hint, int splits_hint, cudaStream_t stream) {
+
   ABCGPT_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M,N,K must be positive (got %d,%d,%d)", M, N, K);
   ABCGPT_CHECK_ARG(N % 8 == 0, "gemm: N must be a multiple of 8 (pad the output; got %d)", N);
   ABCGPT_CHECK_ARG(c != nullptr, "gemm: null output");
@@ -417,7 +444,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   p.M = M; p.N = N; p.K = K;
   p.num_m_blk = num_m_blk; p.num_n_blk = num_n_blk; p.num_k_blk = num_k_blk;
   p.splits = splits; p.kb_per_split = kb_per_split;
-  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias;
+  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.stats = g_gemm_stats;
 
   const long long total = static_cast<long long>(num_m_blk) * num_n_blk * splits;
   const int grid = static_cast<int>(total < sms ? total : sms);

@@ -75,8 +75,8 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int NV, bool HAS_BIAS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
               float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ dw, float* __restrict__ db,
@@ -85,39 +85,45 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = C >> 2;
-  float4 gw[NV], accw[NV], accb[NV];
+  // Register budget (<= 128 so that two 256-thread blocks are resident per SM): the row (x fp32, dy packed bf16)
+  // and the dweight partials stay in registers; gamma is re-read from L1 in both passes instead of being held.
+  float4 accw[NV];
+  float4 accb[HAS_BIAS ? NV : 1];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int idx = lane + 32 * i;
-    gw[i] = (idx < nvec) ? __ldg(reinterpret_cast<const float4*>(w) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-    accw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    accb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int i = 0; i < NV; ++i) accw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < (HAS_BIAS ? NV : 1); ++i) accb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float invC = 1.0f / static_cast<float>(C);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
   for (int row = blockIdx.x * kWarpsPerBlock + warp; row < M; row += gridDim.x * kWarpsPerBlock) {
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<long long>(row) * C);
     const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
-    float4 xh[NV], g[NV];
-    float s1 = 0.f, s2 = 0.f;
+    float4 xv[NV];
+    uint2 dv[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nvec) {
-        const float4 xv = __ldg(xr + idx);
-        const uint2 d = __ldg(dyr + idx);
-        const float4 dyv = make_float4(ptx::bf16lo(d.x), ptx::bf16hi(d.x), ptx::bf16lo(d.y), ptx::bf16hi(d.y));
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(dyv.x * gw[i].x, dyv.y * gw[i].y, dyv.z * gw[i].z, dyv.w * gw[i].w);
-        s1 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-        s2 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        accw[i].x += dyv.x * xh[i].x; accw[i].y += dyv.y * xh[i].y;
-        accw[i].z += dyv.z * xh[i].z; accw[i].w += dyv.w * xh[i].w;
-        accb[i].x += dyv.x; accb[i].y += dyv.y; accb[i].z += dyv.z; accb[i].w += dyv.w;
+        xv[i] = __ldg(xr + idx);
+        dv[i] = __ldg(dyr + idx);
       } else {
-        xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        g[i] = xh[i];
+        xv[i] = make_float4(mu, mu, mu, mu);
+        dv[i] = make_uint2(0u, 0u);
       }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + 32 * i;
+      const float4 gw = (idx < nvec) ? __ldg(w4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 dyv = make_float4(ptx::bf16lo(dv[i].x), ptx::bf16hi(dv[i].x), ptx::bf16lo(dv[i].y), ptx::bf16hi(dv[i].y));
+      const float4 xh = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);
+      const float4 g = make_float4(dyv.x * gw.x, dyv.y * gw.y, dyv.z * gw.z, dyv.w * gw.w);
+      s1 += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+      s2 += (g.x + g.y) + (g.z + g.w);
+      accw[i].x += dyv.x * xh.x; accw[i].y += dyv.y * xh.y; accw[i].z += dyv.z * xh.z; accw[i].w += dyv.w * xh.w;
+      if (HAS_BIAS) { accb[i].x += dyv.x; accb[i].y += dyv.y; accb[i].z += dyv.z; accb[i].w += dyv.w; }
     }
     const float c1 = warp_sum(s1) * invC;
     const float c2 = warp_sum(s2) * invC;
@@ -128,11 +134,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
     for (int i = 0; i < NV; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nvec) {
+        const float4 gw = __ldg(w4 + idx);
+        const float4 dyv = make_float4(ptx::bf16lo(dv[i].x), ptx::bf16hi(dv[i].x), ptx::bf16lo(dv[i].y), ptx::bf16hi(dv[i].y));
         float4 o;
-        o.x = (g[i].x - c2 - xh[i].x * c1) * rs;
-        o.y = (g[i].y - c2 - xh[i].y * c1) * rs;
-        o.z = (g[i].z - c2 - xh[i].z * c1) * rs;
-        o.w = (g[i].w - c2 - xh[i].w * c1) * rs;
+        o.x = (dyv.x * gw.x - c2 - (xv[i].x - mu) * rs * c1) * rs;
+        o.y = (dyv.y * gw.y - c2 - (xv[i].y - mu) * rs * c1) * rs;
+        o.z = (dyv.z * gw.z - c2 - (xv[i].z - mu) * rs * c1) * rs;
+        o.w = (dyv.w * gw.w - c2 - (xv[i].w - mu) * rs * c1) * rs;
         if (drr) {
           const float4 r = __ldg(drr + idx);
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -144,14 +152,14 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
   }
   // block-level reduction of the per-warp dweight / dbias partials, then one atomic per column per block
   float4* redv = reinterpret_cast<float4*>(red);
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (HAS_BIAS ? 2 : 1); ++pass) {
     float* dst = pass == 0 ? dw : db;
     if (dst == nullptr) continue;  // uniform across the block
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int idx = lane + 32 * i;
-      if (idx < nvec) redv[warp * nvec + idx] = pass == 0 ? accw[i] : accb[i];
+      if (idx < nvec) redv[warp * nvec + idx] = (pass == 0 || !HAS_BIAS) ? accw[i] : accb[HAS_BIAS ? i : 0];
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -197,20 +205,20 @@ int layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, cons
   ABCGPT_CHECK_ARG(dy_bf16 && x && weight && mean && rstd && dx_out, "layernorm_bwd: null pointer");
   const int nv = (C + 127) / 128;
   int grid = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int cap = sm_count() * 4;
+  const int cap = sm_count() * 2;  // two resident blocks per SM, grid-stride over rows
   if (grid > cap) grid = cap;
   const size_t smem = static_cast<size_t>(kWarpsPerBlock) * C * sizeof(float);
+  const bool has_bias = dbias != nullptr;
   LN_DISPATCH(nv, {
-    if (smem > 48 * 1024) {
-      static bool done = false;
-      if (!done) {
-        ABCGPT_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        done = true;
-      }
-    }
-    ln_bwd_kernel<NV><<<grid, kWarpsPerBlock * 32, smem, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, weight, mean, rstd, dresid_in, dx_out,
-        reinterpret_cast<__nv_bfloat16*>(dx_bf16), dweight, dbias, M, C);
+    auto launch = [&](auto kern) -> int {
+      if (smem > 48 * 1024) ABCGPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      kern<<<grid, kWarpsPerBlock * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, weight, mean,
+                                                        rstd, dresid_in, dx_out,
+                                                        reinterpret_cast<__nv_bfloat16*>(dx_bf16), dweight, dbias, M, C);
+      return 0;
+    };
+    int rc = has_bias ? launch(ln_bwd_kernel<NV, true>) : launch(ln_bwd_kernel<NV, false>);
+    if (rc) return rc;
   });
   return launch_status("ln_bwd_kernel");
 }

@@ -254,7 +254,7 @@ class GPT(nn.Module):
     # ------------------------------------------------------------------------------------------------------
     # launch plans
     # ------------------------------------------------------------------------------------------------------
-    def _buffers(self, B, T, keep):
+    def _act_buffers(self, B, T, keep):
         key = (B, T, keep)
         if key not in self._bufs:
             self._bufs[key] = _Buffers(self.config, B, T, self._arena["flat"].device, keep)
@@ -272,7 +272,7 @@ class GPT(nn.Module):
         top = self._arena["top"]
         B, T = idx.shape
         assert T <= cfg.block_size, f"Cannot forward sequence of length {T}, block size is only {cfg.block_size}"
-        bufs = self._buffers(B, T, keep_activations)
+        bufs = self._act_buffers(B, T, keep_activations)
         C, H, V = cfg.n_embd, cfg.n_head, cfg.vocab_size
         idx = idx.contiguous()
         ops.embed_fwd(idx, top["wte"][0], top["wpe"][0], bufs.x[0], T)

@@ -121,6 +121,10 @@ int abcgpt_colsum_bf16(const void* dy, int64_t ld, int M, int N, float* out, voi
  */
 int abcgpt_argmax(const void* logits, int64_t ldl, int V, int64_t* out, int64_t out_stride, int B, void* stream);
 
+/* Debug aid: device pointer to 8 uint64 cycle counters accumulated by subsequent GEMM launches (NULL disables):
+ * [0] producer empty-wait [1] MMA full-wait [2] MMA tmem-empty wait [3] epilogue tmem-full wait [5] CTA total. */
+int abcgpt_debug_gemm_stats(void* device_counters);
+
 #ifdef __cplusplus
 }
 #endif
