@@ -38,6 +38,7 @@ struct GemmParams {
   const void* aux;
   long long ldaux;
   const float* bias;
+  int wide;  // 1: every epilogue pointer / leading dimension is 32-byte aligned -> 256-bit global accesses
   unsigned long long* stats;  // optional debug counters (cycles): [0] producer empty-wait, [1] mma full-wait,
                               // [2] mma tmem-empty wait, [3] epilogue tmem-full wait, [4] epilogue busy, [5] cta total
 };
@@ -53,36 +54,92 @@ struct Cfg {
 };
 
 // ---- GELU (exact-erf form of nn.GELU(), model.py:83) ---------------------------------------------------
-// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, i.e. fp32-erff class accuracy) so that erf and the
-// Gaussian pdf share ONE exponential: erf(x/sqrt2) = 1 - poly(t) * exp(-x^2/2).
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = __expf(-0.5f * x * x);
-  const float erf_abs = 1.0f - poly * e;
-  const float erfv = copysignf(erf_abs, x);
-  cdf = 0.5f * (1.0f + erfv);
-  pdf = e * 0.39894228040143268f;
+// Phi(x) = 0.5 (1 + erf(x / sqrt2)) with erf(z) = z * P(t), t = 2 z^2 / 3.5^2 - 1, |z| clamped to 3.5 (erf(3.5) = 1 - 7e-7):
+// a degree-12 Chebyshev-derived polynomial, |Phi error| < 4e-7 in fp32 (the class of erff itself), evaluated on
+// the packed fp32x2 FMA pipe for two columns at a time.  No MUFU in the forward; the backward adds one ex2 per
+// element for the Gaussian pdf.  The epilogue warps are issue-bound, so instruction count is what matters here.
+__device__ __forceinline__ float2 gelu_cdf2(float2 x) {
+  const float2 z = __fmul2_rn(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 zc = make_float2(fminf(fmaxf(z.x, -3.5f), 3.5f), fminf(fmaxf(z.y, -3.5f), 3.5f));
+  const float2 t = __ffma2_rn(__fmul2_rn(zc, zc), make_float2(0.16326530612244897f, 0.16326530612244897f),
+                              make_float2(-1.0f, -1.0f));
+  float2 acc = make_float2(1.783549204e-03f, 1.783549204e-03f);
+#define ABCGPT_HORNER(c) acc = __ffma2_rn(acc, t, make_float2(c, c))
+  ABCGPT_HORNER(-4.138993458e-03f);
+  ABCGPT_HORNER(3.642286241e-03f);
+  ABCGPT_HORNER(-6.848857084e-03f);
+  ABCGPT_HORNER(1.790029780e-02f);
+  ABCGPT_HORNER(-3.037289646e-02f);
+  ABCGPT_HORNER(4.461858910e-02f);
+  ABCGPT_HORNER(-6.463799105e-02f);
+  ABCGPT_HORNER(8.848482037e-02f);
+  ABCGPT_HORNER(-1.146334766e-01f);
+  ABCGPT_HORNER(1.467439851e-01f);
+  ABCGPT_HORNER(-2.007001497e-01f);
+  ABCGPT_HORNER(4.038730577e-01f);
+#undef ABCGPT_HORNER
+  const float2 e = __fmul2_rn(zc, acc);
+  return __ffma2_rn(e, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
 }
-__device__ __forceinline__ float gelu_fwd(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return x * cdf;
-}
-__device__ __forceinline__ float gelu_bwd(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return fmaf(x, pdf, cdf);
+__device__ __forceinline__ float2 gelu_fwd2(float2 x) { return __fmul2_rn(x, gelu_cdf2(x)); }
+__device__ __forceinline__ float2 gelu_bwd2(float2 x) {
+  const float2 cdf = gelu_cdf2(x);
+  const float2 xx = __fmul2_rn(x, x);
+  // pdf = exp(-x^2/2) / sqrt(2 pi) = 2^(-x^2 * 0.5 log2e) * 0.39894228
+  float2 pdf;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pdf.x) : "f"(xx.x * -0.72134752044448170f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pdf.y) : "f"(xx.y * -0.72134752044448170f));
+  pdf = __fmul2_rn(pdf, make_float2(0.39894228040143268f, 0.39894228040143268f));
+  return __ffma2_rn(x, pdf, cdf);
 }
 
 // ---- epilogues: one thread owns 32 consecutive columns of one output row -------------------------------
+// Auxiliary inputs (the fp32 residual for RESID, the bf16 pre-activation for DGELU) do not depend on the
+// accumulator, so they are fetched BEFORE the thread blocks on the accumulator barrier: their DRAM latency hides
+// behind the main loop instead of adding to the epilogue.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, uint32_t (&r)[32]) {
+struct AuxChunk {
+  // RESID: 32 fp32 = 4 x 32 B; DGELU: 32 bf16 = 2 x 32 B
+  static constexpr int N = (EPI == ABCGPT_EPI_RESID) ? 4 : ((EPI == ABCGPT_EPI_DGELU) ? 2 : 1);
+  ptx::u32x8 v[N];
+};
+
+template <int EPI>
+__device__ __forceinline__ void load_aux(AuxChunk<EPI>& a, const GemmParams& p, int row, int col0) {
+  if constexpr (EPI == ABCGPT_EPI_RESID || EPI == ABCGPT_EPI_DGELU) {
+    constexpr int EB = (EPI == ABCGPT_EPI_RESID) ? 4 : 2;  // element bytes
+    constexpr int PER = 32 / EB;                            // elements per 32-byte group
+    const char* base = reinterpret_cast<const char*>(p.aux) + (static_cast<long long>(row) * p.ldaux + col0) * EB;
+#pragma unroll
+    for (int j = 0; j < AuxChunk<EPI>::N; ++j) {
+      const int c = col0 + j * PER;
+      if (row < p.M && c + PER <= p.N && p.wide) {
+        a.v[j] = ptx::ldg256(base + 32 * j);
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 t = make_uint4(0u, 0u, 0u, 0u);
+          if (row < p.M && c + h * (PER / 2) < p.N) t = __ldg(reinterpret_cast<const uint4*>(base + 32 * j + 16 * h));
+          a.v[j].v[4 * h + 0] = t.x; a.v[j].v[4 * h + 1] = t.y; a.v[j].v[4 * h + 2] = t.z; a.v[j].v[4 * h + 3] = t.w;
+        }
+      }
+    }
+  }
+}
+
+// store 16 bf16 columns (8 packed words) starting at column 16*j of the chunk; ncols is a multiple of 8
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* c, int j, int ncols, bool wide, const uint32_t* pk) {
+  if (16 * j + 16 <= ncols && wide) {
+    ptx::stg256(c + 16 * j, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+  } else {
+    if (16 * j < ncols) reinterpret_cast<uint4*>(c + 16 * j)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    if (16 * j + 8 < ncols) reinterpret_cast<uint4*>(c + 16 * j)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, uint32_t (&r)[32],
+                                               const AuxChunk<EPI>& aux) {
   if (row >= p.M || col0 >= p.N) return;
   float v[32];
 #pragma unroll
@@ -96,63 +153,53 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
 
   if constexpr (EPI == ABCGPT_EPI_BF16 || EPI == ABCGPT_EPI_GELU || EPI == ABCGPT_EPI_DGELU) {
     __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
+    uint32_t pk[16];
     if constexpr (EPI == ABCGPT_EPI_DGELU) {
-      const uint4* hp =
-          reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<long long>(row) * p.ldaux + col0);
+      // dH = bf16(acc) * gelu'(h): the reference's gelu_backward sees the bf16 dgrad output and the bf16 h
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (8 * j < ncols) {
-          const uint4 h = __ldg(hp + j);
-          const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            v[8 * j + 2 * q] = ptx::bf16_round(v[8 * j + 2 * q]) * gelu_bwd(ptx::bf16lo(hw[q]));
-            v[8 * j + 2 * q + 1] = ptx::bf16_round(v[8 * j + 2 * q + 1]) * gelu_bwd(ptx::bf16hi(hw[q]));
-          }
-        }
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t hw = aux.v[i >> 3].v[i & 7];
+        const uint32_t db = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        const float2 d = __fmul2_rn(make_float2(ptx::bf16lo(db), ptx::bf16hi(db)),
+                                    gelu_bwd2(make_float2(ptx::bf16lo(hw), ptx::bf16hi(hw))));
+        pk[i] = ptx::pack_bf16x2(d.x, d.y);
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (8 * j < ncols) {
-        uint4 o;
-        o.x = ptx::pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        reinterpret_cast<uint4*>(c)[j] = o;
-      }
-    }
+    for (int j = 0; j < 2; ++j) store_bf16x16(c, j, ncols, p.wide, pk + 8 * j);
     if constexpr (EPI == ABCGPT_EPI_GELU) {
       __nv_bfloat16* g = reinterpret_cast<__nv_bfloat16*>(p.c2) + static_cast<long long>(row) * p.ldc2 + col0;
+      uint32_t gk[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (8 * j < ncols) {
-          float a[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) a[q] = gelu_fwd(ptx::bf16_round(v[8 * j + q]));
-          uint4 o;
-          o.x = ptx::pack_bf16x2(a[0], a[1]);
-          o.y = ptx::pack_bf16x2(a[2], a[3]);
-          o.z = ptx::pack_bf16x2(a[4], a[5]);
-          o.w = ptx::pack_bf16x2(a[6], a[7]);
-          reinterpret_cast<uint4*>(g)[j] = o;
-        }
+      for (int i = 0; i < 16; ++i) {
+        const float2 a = gelu_fwd2(make_float2(ptx::bf16lo(pk[i]), ptx::bf16hi(pk[i])));  // GELU of the bf16 h
+        gk[i] = ptx::pack_bf16x2(a.x, a.y);
       }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) store_bf16x16(g, j, ncols, p.wide, gk + 8 * j);
     }
   } else if constexpr (EPI == ABCGPT_EPI_RESID) {
     // x_out(fp32) = x_in(fp32) + bf16(acc): the reference adds the bf16 Linear output into the fp32 stream
-    const float4* xin = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + static_cast<long long>(row) * p.ldaux + col0);
-    float4* xout = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + col0);
+    float* xout = reinterpret_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (4 * j < ncols) {
-        float4 x = __ldg(xin + j);
-        x.x += ptx::bf16_round(v[4 * j + 0]);
-        x.y += ptx::bf16_round(v[4 * j + 1]);
-        x.z += ptx::bf16_round(v[4 * j + 2]);
-        x.w += ptx::bf16_round(v[4 * j + 3]);
-        xout[j] = x;
+    for (int j = 0; j < 4; ++j) {  // 8 columns per 32-byte group
+      if (8 * j < ncols) {
+        uint32_t o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t b = ptx::pack_bf16x2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+          o[2 * q] = __float_as_uint(__uint_as_float(aux.v[j].v[2 * q]) + ptx::bf16lo(b));
+          o[2 * q + 1] = __float_as_uint(__uint_as_float(aux.v[j].v[2 * q + 1]) + ptx::bf16hi(b));
+        }
+        if (p.wide) {
+          ptx::stg256(xout + 8 * j, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+        } else {
+          reinterpret_cast<uint4*>(xout + 8 * j)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          reinterpret_cast<uint4*>(xout + 8 * j)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
       }
     }
   } else if constexpr (EPI == ABCGPT_EPI_F32_RED) {
@@ -317,16 +364,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n_blk = tile % p.num_n_blk;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int row = m_blk * BM + quarter * 32 + lane;
+      const int col_base = n_blk * BN + half * COLS_PER_WARP;
+      constexpr int NCH = COLS_PER_WARP / 32;
+      AuxChunk<EPI> aux[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) load_aux<EPI>(aux[c], p, row, col_base + c * 32);
       timed_wait(&tfull[as], aphase, 4, p.stats, 3, w0);
       ptx::tc_fence_after();
-      const int row = m_blk * BM + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 32) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         uint32_t r[32];
-        ptx::tmem_ld32(taddr + c, r);
+        ptx::tmem_ld32(taddr + c * 32, r);
         ptx::tmem_ld_wait();
-        epilogue_chunk<EPI>(p, row, n_blk * BN + half * COLS_PER_WARP + c, r);
+        epilogue_chunk<EPI>(p, row, col_base + c * 32, r, aux[c]);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -379,6 +431,222 @@ int dispatch_major(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CU
   return fail(-1, "GEMM operand combination A=MN-major,B=K-major is not instantiated");
 }
 
+
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster compute one 256 x 256 output tile.  Each CTA stages its own
+// 128 rows of A and its own 128 rows (half of N) of B, so per-CTA operand traffic from L2 drops from 48 KB to 32 KB per
+// 64-deep k-block and the ring gets 6 stages; the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), which reads
+// both CTAs' shared memory and writes both CTAs' TMEM.  Barrier protocol:
+//   full[s]    (leader)  1 arrival (leader's expect_tx for BOTH CTAs' bytes) + complete_tx from both CTAs' TMA
+//   empty[s]   (each)    tcgen05.commit multicast to both CTAs
+//   tfull[a]   (each)    tcgen05.commit multicast to both CTAs
+//   tempty[a]  (leader)  2 x 8 epilogue warps (the peer's arrive remotely)
+// =====================================================================================================================
+struct Cfg2 {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = BM * BK * 2;         // 128 rows of A per CTA
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;   // 128 of the 256 B rows per CTA
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C = Cfg2;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], 2 * kNumEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // barrier inits + TMEM allocations of BOTH CTAs are visible before anything is signalled
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m_pair = (p.num_m_blk + 1) / 2;
+  const int total_work = num_m_pair * p.num_n_blk * p.splits;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = pair_id; w < total_work; w += num_pairs) {
+        const int split = w % p.splits;
+        const int tile = w / p.splits;
+        const int m0 = (tile / p.num_n_blk) * 256 + static_cast<int>(rank) * 128;
+        const int n0 = (tile % p.num_n_blk) * BN + static_cast<int>(rank) * (BN / 2);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1, 41);
+          const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+          if (leader) ptx::mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          if constexpr (!A_MN) {
+            ptx::tma_load_2d_2sm(sa, &tmA, full_leader, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) ptx::tma_load_2d_2sm(sa + a * (BK * 128), &tmA, full_leader, m0 + a * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            ptx::tma_load_2d_2sm(sb, &tmB, full_leader, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) ptx::tma_load_2d_2sm(sb + b * (BK * 128), &tmB, full_leader, n0 + b * 64, kb * BK);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = pair_id; w < total_work; w += num_pairs, ++it) {
+        const int split = w % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tempty[as], aphase ^ 1, 42);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full[stage], phase, 43);
+          ptx::tc_fence_after();
+          const uint32_t a_base = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_base = a_base + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? ptx::umma_smem_desc(a_base + k * 2048, BK * 128, 1024)
+                                        : ptx::umma_smem_desc(a_base + k * 32, 0, 1024);
+            const uint64_t bdesc = B_MN ? ptx::umma_smem_desc(b_base + k * 2048, BK * 128, 1024)
+                                        : ptx::umma_smem_desc(b_base + k * 32, 0, 1024);
+            ptx::umma_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit_2sm(&empty[stage], 3);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit_2sm(&tfull[as], 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int COLS_PER_WARP = BN / 2;
+    int it = 0;
+    for (int w = pair_id; w < total_work; w += num_pairs, ++it) {
+      const int tile = w / p.splits;
+      const int m0 = (tile / p.num_n_blk) * 256 + static_cast<int>(rank) * 128;
+      const int n_blk = tile % p.num_n_blk;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int row = m0 + quarter * 32 + lane;
+      const int col_base = n_blk * BN + half * COLS_PER_WARP;
+      constexpr int NCH = COLS_PER_WARP / 32;
+      AuxChunk<EPI> aux[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) load_aux<EPI>(aux[c], p, row, col_base + c * 32);
+      ptx::mbar_wait(&tfull[as], aphase, 44);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        epilogue_chunk<EPI>(p, row, col_base + c * 32, r, aux[c]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[as]), 0));
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t stream) {
+  auto kern = gemm2_kernel<A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    ABCGPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, Cfg2::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return launch_status("gemm2_kernel");
+}
+
+template <bool A_MN, bool B_MN>
+int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+                  cudaStream_t stream) {
+  switch (epi) {
+    case ABCGPT_EPI_BF16: return launch2<A_MN, B_MN, ABCGPT_EPI_BF16>(tmA, tmB, p, grid, stream);
+    case ABCGPT_EPI_GELU: return launch2<A_MN, B_MN, ABCGPT_EPI_GELU>(tmA, tmB, p, grid, stream);
+    case ABCGPT_EPI_RESID: return launch2<A_MN, B_MN, ABCGPT_EPI_RESID>(tmA, tmB, p, grid, stream);
+    case ABCGPT_EPI_DGELU: return launch2<A_MN, B_MN, ABCGPT_EPI_DGELU>(tmA, tmB, p, grid, stream);
+    case ABCGPT_EPI_F32_RED: return launch2<A_MN, B_MN, ABCGPT_EPI_F32_RED>(tmA, tmB, p, grid, stream);
+    case ABCGPT_EPI_F32: return launch2<A_MN, B_MN, ABCGPT_EPI_F32>(tmA, tmB, p, grid, stream);
+  }
+  return fail(-1, "unknown GEMM epilogue %d", epi);
+}
+
+int dispatch_major2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                    int grid, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return dispatch_epi2<false, false>(epi, tmA, tmB, p, grid, stream);
+  if (!a_mn && b_mn) return dispatch_epi2<false, true>(epi, tmA, tmB, p, grid, stream);
+  if (a_mn && b_mn) return dispatch_epi2<true, true>(epi, tmA, tmB, p, grid, stream);
+  return fail(-1, "GEMM operand combination A=MN-major,B=K-major is not instantiated");
+}
+
 }  // namespace
 
 int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, long long ldb, int M, int N, int K,
@@ -392,35 +660,45 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   ABCGPT_CHECK_ARG((epi != ABCGPT_EPI_RESID && epi != ABCGPT_EPI_DGELU) || aux != nullptr,
                    "gemm: epilogue %d needs the aux input", epi);
 
-  // tile-N choice: the widest tile that keeps the persistent schedule's last wave reasonably full
+  // Tile choice.  bn_hint: 0 = auto, 128 / 256 = one CTA per 128 x bn tile, 512 = CTA pair per 256 x 256 tile.
   const int sms = sm_count();
   const int num_m_blk = (M + BM - 1) / BM;
   const int num_k_blk = (K + BK - 1) / BK;
   int bn = bn_hint;
   if (bn == 0) {
-    double best = -1.0;
-    const int cands[2] = {256, 128};
-    for (int ci = 0; ci < 2; ++ci) {
-      const int cbn = cands[ci];
-      if (cbn == 256 && N <= 128) continue;
-      const long long tiles = static_cast<long long>(num_m_blk) * ((N + cbn - 1) / cbn);
-      const long long waves = (tiles + sms - 1) / sms;
-      // useful fraction of MMA issue slots: quantisation x padded-N waste, with a mild preference for 256
-      const double eff = (static_cast<double>(tiles) / (waves * sms)) * (static_cast<double>(N) / (((N + cbn - 1) / cbn) * cbn)) *
-                         (cbn == 256 ? 1.0 : 0.93);
-      if (eff > best) {
-        best = eff;
-        bn = cbn;
-      }
+    // CTA pairs halve the B-operand traffic per SM (the single-CTA kernel is starved by L2->SM operand delivery);
+    // they need N > 128 to be worth a 256-wide tile.
+    if (N > 128) {
+      bn = 512;
+    } else {
+      bn = 128;
     }
   }
-  ABCGPT_CHECK_ARG(bn == 128 || bn == 256, "gemm: unsupported tile N %d", bn);
-  const int num_n_blk = (N + bn - 1) / bn;
+  ABCGPT_CHECK_ARG(bn == 128 || bn == 256 || bn == 512, "gemm: unsupported tile hint %d", bn);
+  const bool pair = bn == 512;
+  const int tile_n = pair ? 256 : bn;
+  const int num_n_blk = (N + tile_n - 1) / tile_n;
+  const int num_m_units = pair ? (num_m_blk + 1) / 2 : num_m_blk;  // schedulable row blocks
+  const int units = pair ? sms / 2 : sms;                           // schedulable CTAs / CTA pairs
 
   int splits = 1;
   if (epi == ABCGPT_EPI_F32_RED) {
-    const long long tiles = static_cast<long long>(num_m_blk) * num_n_blk;
-    splits = splits_hint > 0 ? splits_hint : static_cast<int>((2LL * sms + tiles - 1) / tiles);
+    // split-K so that the persistent schedule's last wave is full: minimise rounds(s) * (k-blocks per split + a fixed
+    // per-work-item cost for the reduction epilogue)
+    const long long tiles = static_cast<long long>(num_m_units) * num_n_blk;
+    if (splits_hint > 0) {
+      splits = splits_hint;
+    } else {
+      long long best = -1;
+      for (int sp = 1; sp <= 64 && sp <= num_k_blk; ++sp) {
+        const long long rounds = (tiles * sp + units - 1) / units;
+        const long long cost = rounds * ((num_k_blk + sp - 1) / sp + 6);
+        if (best < 0 || cost < best) {
+          best = cost;
+          splits = sp;
+        }
+      }
+    }
     if (splits > num_k_blk) splits = num_k_blk;
     if (splits < 1) splits = 1;
   }
@@ -435,7 +713,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
     rc = encode_tmap_2d(&tmA, a, 2, M, K, lda * 2, 64, BK, true);
   if (rc) return rc;
   if (!b_mn)
-    rc = encode_tmap_2d(&tmB, b, 2, K, N, ldb * 2, BK, bn, true);
+    rc = encode_tmap_2d(&tmB, b, 2, K, N, ldb * 2, BK, pair ? 128 : bn, true);
   else
     rc = encode_tmap_2d(&tmB, b, 2, N, K, ldb * 2, 64, BK, true);
   if (rc) return rc;
@@ -445,8 +723,20 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   p.num_m_blk = num_m_blk; p.num_n_blk = num_n_blk; p.num_k_blk = num_k_blk;
   p.splits = splits; p.kb_per_split = kb_per_split;
   p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.stats = g_gemm_stats;
+  {
+    const bool f32_out = (epi == ABCGPT_EPI_RESID || epi == ABCGPT_EPI_F32 || epi == ABCGPT_EPI_F32_RED);
+    const long long cb = f32_out ? 4 : 2, ab = (epi == ABCGPT_EPI_RESID) ? 4 : 2;
+    bool ok = (reinterpret_cast<uintptr_t>(c) % 32 == 0) && ((ldc * cb) % 32 == 0);
+    if (c2) ok = ok && (reinterpret_cast<uintptr_t>(c2) % 32 == 0) && ((ldc2 * 2) % 32 == 0);
+    if (aux) ok = ok && (reinterpret_cast<uintptr_t>(aux) % 32 == 0) && ((ldaux * ab) % 32 == 0);
+    p.wide = ok ? 1 : 0;
+  }
 
-  const long long total = static_cast<long long>(num_m_blk) * num_n_blk * splits;
+  const long long total = static_cast<long long>(num_m_units) * num_n_blk * splits;
+  if (pair) {
+    const int grid = 2 * static_cast<int>(total < units ? total : units);
+    return dispatch_major2(a_mn, b_mn, epi, tmA, tmB, p, grid, stream);
+  }
   const int grid = static_cast<int>(total < sms ? total : sms);
   if (bn == 256) return dispatch_major<256>(a_mn, b_mn, epi, tmA, tmB, p, grid, stream);
   return dispatch_major<128>(a_mn, b_mn, epi, tmA, tmB, p, grid, stream);

@@ -15,7 +15,7 @@ shapes = [("c_attn fwd", M, 3 * C, C, False, False, ops.EPI_BF16), ("c_fc gelu",
           ("dgrad fc", M, C, 4 * C, False, True, ops.EPI_BF16), ("dgrad proj dgelu", M, 4 * C, C, False, True, ops.EPI_DGELU),
           ("wgrad fc", 4 * C, C, M, True, True, ops.EPI_F32_RED), ("wgrad attn", 3 * C, C, M, True, True, ops.EPI_F32_RED)]
 for name, m, n, k, amn, bmn, epi in shapes:
-    for bn in (256, 128):
+    for bn in (512, 256):
         A = torch.randn((k, m) if amn else (m, k), device=dev).bfloat16()
         B = torch.randn((k, n) if bmn else (n, k), device=dev).bfloat16()
         odt = torch.float32 if epi in (ops.EPI_RESID, ops.EPI_F32_RED) else torch.bfloat16

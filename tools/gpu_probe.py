@@ -327,6 +327,15 @@ def build_cases():
         cases[f"gemm_nt_k256_bn{bn}"] = lambda bn=bn: case_gemm(f"gemm_nt_k256_bn{bn}", 256, 512, 256, False, False, E.EPI_BF16, bn, timing=False)
         cases[f"gemm_nn_small_bn{bn}"] = lambda bn=bn: case_gemm(f"gemm_nn_small_bn{bn}", 128, 256, 128, False, True, E.EPI_BF16, bn, timing=False)
         cases[f"gemm_tn_small_bn{bn}"] = lambda bn=bn: case_gemm(f"gemm_tn_small_bn{bn}", 128, 256, 128, True, True, E.EPI_F32, bn, timing=False)
+    cases["gemm2_nt_small"] = lambda: case_gemm("gemm2_nt_small", 256, 256, 64, False, False, E.EPI_BF16, 512, timing=False)
+    cases["gemm2_nt_k512"] = lambda: case_gemm("gemm2_nt_k512", 512, 768, 512, False, False, E.EPI_BF16, 512, timing=False)
+    cases["gemm2_nn"] = lambda: case_gemm("gemm2_nn", 512, 512, 384, False, True, E.EPI_BF16, 512, timing=False)
+    cases["gemm2_tn"] = lambda: case_gemm("gemm2_tn", 512, 512, 1024, True, True, E.EPI_F32, 512, timing=False)
+    cases["gemm2_tn_red"] = lambda: case_gemm("gemm2_tn_red", 768, 768, 8192, True, True, E.EPI_F32_RED, 512, timing=False)
+    cases["gemm2_ragged"] = lambda: case_gemm("gemm2_ragged", 328, 200, 136, False, False, E.EPI_BF16, 512, timing=False)
+    cases["gemm2_gelu"] = lambda: case_gemm("gemm2_gelu", 1024, 1536, 384, False, False, E.EPI_GELU, 512, timing=False)
+    cases["gemm2_resid"] = lambda: case_gemm("gemm2_resid", 1024, 384, 1536, False, False, E.EPI_RESID, 512, timing=False)
+    cases["gemm2_dgelu"] = lambda: case_gemm("gemm2_dgelu", 1024, 1536, 384, False, True, E.EPI_DGELU, 512, timing=False)
     cases["gemm_nt_ragged"] = lambda: case_gemm("gemm_nt_ragged", 200, 96, 136, False, False, E.EPI_BF16, 128, timing=False)
     cases["gemm_nt_f32"] = lambda: case_gemm("gemm_nt_f32", 256, 256, 768, False, False, E.EPI_F32, 256, timing=False)
     cases["gemm_gelu"] = lambda: case_gemm("gemm_gelu", 512, 1536, 384, False, False, E.EPI_GELU, 0, timing=False)
