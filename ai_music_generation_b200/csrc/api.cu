@@ -4,7 +4,7 @@
 #include "kernels.h"
 
 using namespace abcgpt;
-namespace abcgpt { extern unsigned long long* g_gemm_stats; }
+namespace abcgpt { extern unsigned long long* g_gemm_stats; extern long long* g_attn_trace; }
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
 
@@ -79,6 +79,11 @@ int abcgpt_argmax(const void* logits, int64_t ldl, int V, int64_t* out, int64_t 
 /* debug: device pointer to 8 uint64 cycle counters filled by subsequent GEMM launches (NULL disables) */
 int abcgpt_debug_gemm_stats(void* device_counters) {
   abcgpt::g_gemm_stats = reinterpret_cast<unsigned long long*>(device_counters);
+  return 0;
+}
+
+int abcgpt_debug_attn_trace(void* device_stamps) {
+  abcgpt::g_attn_trace = reinterpret_cast<long long*>(device_stamps);
   return 0;
 }
 

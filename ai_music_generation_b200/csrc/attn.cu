@@ -15,6 +15,9 @@
 #include "ptx.cuh"
 
 namespace abcgpt {
+
+long long* g_attn_trace = nullptr;  // debug only (abcgpt_debug_attn_trace): per-phase clock64 stamps of one CTA
+
 namespace {
 
 constexpr int HS = 64;
@@ -188,50 +191,109 @@ __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, c
 // ======================================================================================================
 // forward
 // ======================================================================================================
+// 128 query rows per CTA, K/V streamed in 64-row tiles through a 3-stage ring.  The score tile S (128 x 64 fp32) is
+// double-buffered in TMEM so the tensor core computes S_{j+1} while the softmax threads work on S_j; P is
+// double-buffered in shared memory; O accumulates in TMEM across all tiles (tcgen05.mma accumulate), so the softmax
+// threads never touch O until the end.  That needs a per-row reference exponent that is NOT the running max:
+// m_ref is the true max of the first tile and is only raised (with an in-TMEM rescale of O) when a later tile exceeds
+// it by more than 2^64 -- exact in floating point, because a common power-of-two factor cancels in O / l.
 struct FwdSmem {
   static constexpr int Q = 0;                 // 128 x 64 bf16
-  static constexpr int K = 16384;             // 128 x 64
-  static constexpr int V = 32768;             // 128 x 64
-  static constexpr int P = 49152;             // 2 slabs of 128 x 64
-  static constexpr int BAR = 81920;
-  static constexpr int TOTAL = BAR + 128 + 1024;
+  static constexpr int KV = 16384;            // 3 stages x (K 64x64 | V 64x64)
+  static constexpr int P = 16384 + 3 * 16384; // 2 buffers of 128 x 64 bf16
+  static constexpr int BAR = P + 2 * 16384;
+  static constexpr int TOTAL = BAR + 256 + 1024;
 };
+constexpr float kRescaleThreshold = 64.0f;  // log2 units
+
+// p = 2^(s*sl2 - m_ref) for one 32-column chunk, also tracks the raw row max; MODE as for the other chunk helpers
+template <int MODE>
+__device__ __forceinline__ void fwd_chunk(uint32_t taddr, int lane, float neg_m, float& tmax, float& rowsum, uint32_t* pk) {
+  if (MODE == kMasked) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    return;
+  }
+  uint32_t v[32];
+  ptx::tmem_ld32(taddr, v);
+  ptx::tmem_ld_wait();
+  const float2 sl = make_float2(kSl2, kSl2), nm = make_float2(neg_m, neg_m);
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+  float m0 = tmax, m1 = -1e30f;
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
+    float s2 = __uint_as_float(v[2 * i + 2]), s3 = __uint_as_float(v[2 * i + 3]);
+    if (MODE == kDiag) {
+      s0 = (2 * i <= lane) ? s0 : -1e30f;
+      s1 = (2 * i + 1 <= lane) ? s1 : -1e30f;
+      s2 = (2 * i + 2 <= lane) ? s2 : -1e30f;
+      s3 = (2 * i + 3 <= lane) ? s3 : -1e30f;
+    }
+    m0 = fmaxf(m0, fmaxf(s0, s1));
+    m1 = fmaxf(m1, fmaxf(s2, s3));
+    const float2 t0 = __ffma2_rn(make_float2(s0, s1), sl, nm);
+    const float2 t1 = __ffma2_rn(make_float2(s2, s3), sl, nm);
+    const float2 p0 = make_float2(ex2(t0.x), ex2(t0.y));  // masked entries: 2^(-huge) = 0
+    const float2 p1 = make_float2(ex2(t1.x), ex2(t1.y));
+    acc0 = __fadd2_rn(acc0, p0);
+    acc1 = __fadd2_rn(acc1, p1);
+    pk[i] = ptx::pack_bf16x2(p0.x, p0.y);
+    pk[i + 1] = ptx::pack_bf16x2(p1.x, p1.y);
+  }
+  tmax = fmaxf(m0, m1);
+  rowsum += (acc0.x + acc0.y) + (acc1.x + acc1.y);
+}
+
+__device__ __forceinline__ void fwd_tile(uint32_t tm_s, int lane, int cls0, int cls1, float neg_m, float& tmax, float& rowsum,
+                                         uint32_t* pk) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int cls = c == 0 ? cls0 : cls1;
+    if (cls == kFull) fwd_chunk<kFull>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16);
+    else if (cls == kDiag) fwd_chunk<kDiag>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16);
+    else fwd_chunk<kMasked>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16);
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                int T, int H, int C) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int C, long long* trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = bars + 2;
-  uint64_t* v_full = bars + 3;
-  uint64_t* v_empty = bars + 4;
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint64_t* o_empty = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_full = bars + 1;    // [3]
+  uint64_t* kv_empty = bars + 4;   // [3]
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* p_full = bars + 9;     // [2]
+  uint64_t* p_empty = bars + 11;   // [2]
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_q_tiles = gridDim.x;
-  const int qt = num_q_tiles - 1 - blockIdx.x;
+  const int qt = gridDim.x - 1 - blockIdx.x;
   const int b = blockIdx.y / H, h = blockIdx.y % H;
   const int row0 = b * T + qt * 128;
-  const int num_kv = qt + 1;
+  const int kv_end = min(T, qt * 128 + 128);
+  const int num_kv = (kv_end + 63) / 64;
+  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
+#define ATTN_STAMP(k) do { if (tr) trace[j * 8 + (k)] = clock64(); } while (0)
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmQKV);
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmKV);
     ptx::mbar_init(q_full, 1);
-    ptx::mbar_init(k_full, 1);
-    ptx::mbar_init(k_empty, 1);
-    ptx::mbar_init(v_full, 1);
-    ptx::mbar_init(v_empty, 1);
-    ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(p_full, 128);
+    for (int s = 0; s < 3; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&p_full[s], 128);
+      ptx::mbar_init(&p_empty[s], 1);
+    }
     ptx::mbar_init(o_full, 1);
-    ptx::mbar_init(o_empty, 128);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -242,49 +304,57 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_S = tmem_base;        // 128 columns
-  const uint32_t tm_O = tmem_base + 128;  // 64 columns
+  const uint32_t tm_O = tmem_base + 128;  // S buffers at columns [0,64) and [64,128)
 
   if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_expect_tx(q_full, 16384);
-      ptx::tma_load_2d(smem + FwdSmem::Q, &tmQKV, q_full, h * HS, row0);
+      ptx::tma_load_2d(smem + FwdSmem::Q, &tmQ, q_full, h * HS, row0);
       for (int j = 0; j < num_kv; ++j) {
-        const uint32_t ph = j & 1;
-        ptx::mbar_wait(k_empty, ph ^ 1, 10);
-        ptx::mbar_expect_tx(k_full, 16384);
-        ptx::tma_load_2d(smem + FwdSmem::K, &tmQKV, k_full, C + h * HS, b * T + j * 128);
-        ptx::mbar_wait(v_empty, ph ^ 1, 11);
-        ptx::mbar_expect_tx(v_full, 16384);
-        ptx::tma_load_2d(smem + FwdSmem::V, &tmQKV, v_full, 2 * C + h * HS, b * T + j * 128);
+        const int st = j % 3;
+        const uint32_t ph = (j / 3) & 1;
+        ptx::mbar_wait(&kv_empty[st], ph ^ 1, 10);
+        ptx::mbar_expect_tx(&kv_full[st], 16384);
+        uint8_t* dst = smem + FwdSmem::KV + st * 16384;
+        ptx::tma_load_2d(dst, &tmKV, &kv_full[st], C + h * HS, b * T + j * 64);
+        ptx::tma_load_2d(dst + 8192, &tmKV, &kv_full[st], 2 * C + h * HS, b * T + j * 64);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(128, 64, 0, 1);
-      const uint32_t sQ = ptx::smem_u32(smem + FwdSmem::Q), sK = ptx::smem_u32(smem + FwdSmem::K);
-      const uint32_t sV = ptx::smem_u32(smem + FwdSmem::V), sP = ptx::smem_u32(smem + FwdSmem::P);
+      const uint32_t sQ = ptx::smem_u32(smem + FwdSmem::Q);
+      const uint32_t sKV = ptx::smem_u32(smem + FwdSmem::KV);
+      const uint32_t sP = ptx::smem_u32(smem + FwdSmem::P);
       ptx::mbar_wait(q_full, 0, 12);
+      ptx::mbar_wait(&kv_full[0], 0, 13);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ptx::umma_ss(tmem_base, desc_k(sQ, k), desc_k(sKV, k), idesc_s, k > 0);
+      ptx::umma_commit(&s_full[0]);
       for (int j = 0; j < num_kv; ++j) {
-        const uint32_t ph = j & 1;
-        ptx::mbar_wait(k_full, ph, 13);
-        ptx::tc_fence_after();
+        if (j + 1 < num_kv) {  // S_{j+1} runs on the tensor core while the softmax threads work on S_j
+          const int st = (j + 1) % 3;
+          ptx::mbar_wait(&kv_full[st], ((j + 1) / 3) & 1, 14);
+          ptx::tc_fence_after();
+          const uint32_t sK = sKV + st * 16384;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_S, desc_k(sQ, k), desc_k(sK, k), idesc_s, k > 0);
-        ptx::umma_commit(s_full);
-        ptx::umma_commit(k_empty);
-        ptx::mbar_wait(p_full, ph, 14);
-        ptx::mbar_wait(v_full, ph, 15);
-        ptx::mbar_wait(o_empty, ph ^ 1, 16);
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_ss(tmem_base + ((j + 1) & 1) * 64, desc_k(sQ, k), desc_k(sK, k), idesc_s, k > 0);
+          ptx::umma_commit(&s_full[(j + 1) & 1]);
+        }
+        ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1, 15);
         ptx::tc_fence_after();
+        const uint32_t sV = sKV + (j % 3) * 16384 + 8192;
+        const uint32_t sPj = sP + (j & 1) * 16384;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          ptx::umma_ss(tm_O, desc_k(sP + (k >> 2) * 16384, k & 3), desc_mn(sV, k), idesc_o, k > 0);
-        ptx::umma_commit(o_full);
-        ptx::umma_commit(v_empty);
+        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_O, desc_k(sPj, k), desc_mn(sV, k), idesc_o, (j > 0 || k > 0));
+        ptx::umma_commit(&kv_empty[j % 3]);
+        ptx::umma_commit(&p_empty[j & 1]);
       }
+      ptx::umma_commit(o_full);
     }
     __syncwarp();
   } else {
@@ -292,79 +362,92 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t sP = ptx::smem_u32(smem + FwdSmem::P);
-    float O[HS];
-#pragma unroll
-    for (int i = 0; i < HS; ++i) O[i] = 0.f;
-    float m = -1e30f, l = 0.f;
+    const int r0 = qt * 128 + quarter * 32;  // first query row of this warp (relative to the sequence)
+    float m_ref = 0.f, l = 0.f;
     for (int j = 0; j < num_kv; ++j) {
-      const uint32_t ph = j & 1;
-      const bool diag = (j == qt);
-      ptx::mbar_wait(s_full, ph, 17);
+      const int bsel = j & 1;
+      const uint32_t tm_s = tmem_base + lane_off + bsel * 64;
+      // chunk classes of this warp for key columns [64j, 64j+32) and [64j+32, 64j+64)
+      const int c0 = j * 64, c1 = j * 64 + 32;
+      const int cls0 = (c0 + 31 <= r0) ? kFull : ((c0 > r0 + 31) ? kMasked : kDiag);
+      const int cls1 = (c1 + 31 <= r0) ? kFull : ((c1 > r0 + 31) ? kMasked : kDiag);
+      ATTN_STAMP(0);
+      ptx::mbar_wait(&s_full[bsel], (j >> 1) & 1, 17);
       ptx::tc_fence_after();
-      float mx = -1e30f;
-      if (!diag) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) mx = fmaxf(mx, fwd_chunk_max<kFull>(tm_S + lane_off + c * 32, lane));
+      ATTN_STAMP(1);
+      uint32_t pk[32];
+      float tmax = -1e30f, rowsum = 0.f;
+      if (j == 0) {
+        // first tile: the reference exponent is its true row max (cheap max-only pass, then the exp pass)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int cls = c == 0 ? cls0 : cls1;
+          if (cls == kFull) tmax = fmaxf(tmax, fwd_chunk_max<kFull>(tm_s + c * 32, lane));
+          else if (cls == kDiag) tmax = fmaxf(tmax, fwd_chunk_max<kDiag>(tm_s + c * 32, lane));
+        }
+        m_ref = tmax * kSl2;
+        fwd_tile(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk);
       } else {
-#pragma unroll 1
-        for (int c = 0; c <= quarter; ++c)
-          mx = fmaxf(mx, c < quarter ? fwd_chunk_max<kFull>(tm_S + lane_off + c * 32, lane)
-                                     : fwd_chunk_max<kDiag>(tm_S + lane_off + c * 32, lane));
-      }
-      const float m_new = fmaxf(m, mx * kSl2);
-      const float alpha = ex2(m - m_new);
-      float rowsum = 0.f;
-      if (!diag) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c)
-          rowsum += fwd_chunk_exp<kFull>(tm_S + lane_off + c * 32, lane, -m_new, sP + (c >> 1) * 16384, r, c & 1);
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t ta = tm_S + lane_off + c * 32, slab = sP + (c >> 1) * 16384;
-          if (c < quarter) rowsum += fwd_chunk_exp<kFull>(ta, lane, -m_new, slab, r, c & 1);
-          else if (c == quarter) rowsum += fwd_chunk_exp<kDiag>(ta, lane, -m_new, slab, r, c & 1);
-          else rowsum += fwd_chunk_exp<kMasked>(ta, lane, -m_new, slab, r, c & 1);
+        fwd_tile(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk);
+        const bool need = tmax * kSl2 - m_ref > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: raise the reference, rescale the O accumulator in TMEM, recompute this tile's P
+          const float m_new = need ? tmax * kSl2 : m_ref;
+          const float alpha = ex2(m_ref - m_new);
+          ptx::mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1, 19);  // every earlier P V product has landed in O
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld32(tm_O + lane_off + c * 32, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tmem_st32(tm_O + lane_off + c * 32, o);
+          }
+          ptx::tmem_st_wait();
+          l *= alpha;
+          m_ref = m_new;
+          tmax = -1e30f;
+          rowsum = 0.f;
+          fwd_tile(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk);
         }
       }
-      l = l * alpha + rowsum;
-      m = m_new;
+      l += rowsum;
+      ATTN_STAMP(2);
+      if (j >= 2) ptx::mbar_wait(&p_empty[bsel], ((j >> 1) - 1) & 1, 18);  // P V of tile j-2 has finished reading this buffer
+      ATTN_STAMP(3);
+      st_slab32(sP + bsel * 16384, r, 0, pk);
+      st_slab32(sP + bsel * 16384, r, 1, pk + 16);
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(p_full);
-      ptx::mbar_wait(o_full, ph, 18);
-      ptx::tc_fence_after();
+      ptx::mbar_arrive(&p_full[bsel]);
+      ATTN_STAMP(4);
+    }
+#undef ATTN_STAMP
+    ptx::mbar_wait(o_full, 0, 20);
+    ptx::tc_fence_after();
+    const int t = qt * 128 + r;
+    const float inv = 1.0f / l;
+    __nv_bfloat16* o = out + static_cast<long long>(b * T + t) * C + h * HS;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tm_O + lane_off + c * 32, v);
-        ptx::tmem_ld_wait();
-        const float2 al = make_float2(alpha, alpha);
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld32(tm_O + lane_off + c * 32, v);
+      ptx::tmem_ld_wait();
+      if (t < T) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float2 o = __ffma2_rn(make_float2(O[c * 32 + i], O[c * 32 + i + 1]), al, f2(v[i], v[i + 1]));
-          O[c * 32 + i] = o.x;
-          O[c * 32 + i + 1] = o.y;
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
+          w.y = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
+          w.z = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
+          w.w = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
+          reinterpret_cast<uint4*>(o)[c * 4 + q] = w;
         }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(o_empty);
     }
-    const int t = qt * 128 + r;
-    if (t < T) {
-      const float inv = 1.0f / l;
-      __nv_bfloat16* o = out + static_cast<long long>(b * T + t) * C + h * HS;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint4 w;
-        w.x = ptx::pack_bf16x2(O[8 * q + 0] * inv, O[8 * q + 1] * inv);
-        w.y = ptx::pack_bf16x2(O[8 * q + 2] * inv, O[8 * q + 3] * inv);
-        w.z = ptx::pack_bf16x2(O[8 * q + 4] * inv, O[8 * q + 5] * inv);
-        w.w = ptx::pack_bf16x2(O[8 * q + 6] * inv, O[8 * q + 7] * inv);
-        reinterpret_cast<uint4*>(o)[q] = w;
-      }
-      lse[(static_cast<long long>(b) * H + h) * T + t] = (m + log2f(l)) * kLn2;
-    }
+    if (t < T) lse[(static_cast<long long>(b) * H + h) * T + t] = (m_ref + log2f(l)) * kLn2;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -393,31 +476,42 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
 }
 
 // ======================================================================================================
-// backward: dQ
+// backward: dQ and dK/dV
 // ======================================================================================================
+// Both backward kernels run ONE CTA per SM with two compute groups of 128 threads.  The score tiles S and dP
+// (128 x 64 fp32 each) are double-buffered in TMEM and buffer g belongs to group g: while group 0 turns S/dP of step j
+// into dS, the tensor core already produces S/dP of step j+1 for group 1, and the accumulating MMAs (dQ, or dV and dK)
+// of finished steps interleave in between.  Without this, every step serialises "MMA -> exp/dS -> MMA" (measured:
+// ~1400 of ~2700 cycles per step spent waiting for the score MMAs).
+constexpr int kRing = 6;          // K/V (dQ kernel) or Q/dO (dK/dV kernel) tiles in flight: TMA latency >> one step
+constexpr int kBwdThreads = 352;  // warp 0 TMA, warp 1 score MMAs, warps 2..5 group 0, warps 6..9 group 1, warp 10 accumulating MMAs
+
 struct DqSmem {
-  static constexpr int Q = 0;        // 128 x 64
-  static constexpr int DO = 16384;   // 128 x 64
-  static constexpr int KV = 32768;   // 2 stages x (K 64x64 | V 64x64) = 2 x 16 KB
-  static constexpr int DS = 65536;   // 128 x 64
-  static constexpr int BAR = 81920;
-  static constexpr int TOTAL = BAR + 128 + 1024;
+  static constexpr int Q = 0;         // 128 x 64
+  static constexpr int DO = 16384;    // 128 x 64
+  static constexpr int KV = 32768;    // kRing stages x (K 64x64 | V 64x64)
+  static constexpr int DS = KV + kRing * 16384;  // 2 buffers x 128 x 64
+  static constexpr int BAR = DS + 2 * 16384;
+  static constexpr int TOTAL = BAR + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                    const __grid_constant__ CUtensorMap tmDO128, const float* __restrict__ lse,
-                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C) {
+                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, long long* trace) {
+  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
+#define DQ_STAMP(k) do { if (tr) trace[j * 8 + (k)] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DqSmem::BAR);
   uint64_t* qdo_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* ds_full = bars + 6;
-  uint64_t* dq_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;                 // [kRing]
+  uint64_t* kv_empty = kv_full + kRing;         // [kRing]
+  uint64_t* s_full = kv_empty + kRing;          // [2]
+  uint64_t* ds_full = s_full + 2;               // [2]
+  uint64_t* dq_done = ds_full + 2;              // [2]
+  uint64_t* all_done = dq_done + 2;  // dedicated: a parity wait is only meaningful to a thread that followed every phase
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;
@@ -431,24 +525,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     ptx::prefetch_tmap(&tmQKV64);
     ptx::prefetch_tmap(&tmDO128);
     ptx::mbar_init(qdo_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kRing; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
       ptx::mbar_init(&kv_empty[s], 1);
     }
-    ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(ds_full, 128);
-    ptx::mbar_init(dq_done, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&ds_full[s], 128);
+      ptx::mbar_init(&dq_done[s], 1);
+    }
+    ptx::mbar_init(all_done, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 64, tm_dQ = tmem_base + 128;
+  const uint32_t tm_dQ = tmem_base + 256;  // S_g at 128 g, dP_g at 128 g + 64
 
   if (warp == 0) {
     if (lane == 0) {
@@ -456,8 +553,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
       ptx::tma_load_2d(smem + DqSmem::Q, &tmQKV128, qdo_full, h * HS, row0);
       ptx::tma_load_2d(smem + DqSmem::DO, &tmDO128, qdo_full, h * HS, row0);
       for (int j = 0; j < num_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % kRing;
+        const uint32_t ph = (j / kRing) & 1;
         ptx::mbar_wait(&kv_empty[st], ph ^ 1, 20);
         ptx::mbar_expect_tx(&kv_full[st], 16384);
         uint8_t* dst = smem + DqSmem::KV + st * 16384;
@@ -467,69 +564,289 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     }
     __syncwarp();
   } else if (warp == 1) {
+    // ---- score MMAs: S_j = Q K_j^T, dP_j = dO V_j^T into TMEM buffer j & 1 (one issuing thread per MMA family:
+    // a single thread issuing all twelve MMAs of a step plus its barrier traffic was the bottleneck)
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_dq = ptx::umma_idesc_bf16(128, 64, 0, 1);
-      const uint32_t sQ = ptx::smem_u32(smem + DqSmem::Q), sDO = ptx::smem_u32(smem + DqSmem::DO);
-      const uint32_t sDS = ptx::smem_u32(smem + DqSmem::DS);
+      const uint64_t dQ0 = desc_k(ptx::smem_u32(smem + DqSmem::Q), 0), dDO0 = desc_k(ptx::smem_u32(smem + DqSmem::DO), 0);
+      const uint64_t dKV0 = desc_k(ptx::smem_u32(smem + DqSmem::KV), 0);
       ptx::mbar_wait(qdo_full, 0, 21);
       for (int j = 0; j < num_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const uint32_t sK = ptx::smem_u32(smem + DqSmem::KV + st * 16384), sV = sK + 8192;
-        ptx::mbar_wait(&kv_full[st], ph, 22);
+        ptx::mbar_wait(&kv_full[j % kRing], (j / kRing) & 1, 22);
+        if (j >= 2) ptx::mbar_wait(&ds_full[j & 1], ((j - 2) >> 1) & 1, 23);  // group j&1 has consumed S/dP of step j-2
         ptx::tc_fence_after();
+        const uint64_t dK = dKV0 + static_cast<uint64_t>((j % kRing) * (16384 >> 4)), dV = dK + (8192 >> 4);
+        const uint32_t tS = tmem_base + (j & 1) * 128;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_S, desc_k(sQ, k), desc_k(sK, k), idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) ptx::umma_ss(tS, dQ0 + 2 * k, dK + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dP, desc_k(sDO, k), desc_k(sV, k), idesc_s, k > 0);
-        ptx::umma_commit(s_full);
-        ptx::mbar_wait(ds_full, j & 1, 23);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dQ, desc_k(sDS, k), desc_mn(sK, k), idesc_dq, (j > 0 || k > 0));
-        ptx::umma_commit(&kv_empty[st]);
-        ptx::umma_commit(dq_done);
+        for (int k = 0; k < 4; ++k) ptx::umma_ss(tS + 64, dDO0 + 2 * k, dV + 2 * k, idesc_s, k > 0);
+        ptx::umma_commit(&s_full[j & 1]);
       }
     }
     __syncwarp();
+  } else if (warp == 10) {
+    // ---- accumulating MMAs: dQ += dS_j K_j
+    if (lane == 0) {
+      constexpr uint32_t idesc_dq = ptx::umma_idesc_bf16(128, 64, 0, 1);
+      const uint64_t dDS0 = desc_k(ptx::smem_u32(smem + DqSmem::DS), 0);
+      const uint64_t dKmn0 = desc_mn(ptx::smem_u32(smem + DqSmem::KV), 0);
+      for (int j = 0; j < num_kv; ++j) {
+        ptx::mbar_wait(&ds_full[j & 1], (j >> 1) & 1, 23);
+        ptx::tc_fence_after();
+        const uint64_t dDS = dDS0 + static_cast<uint64_t>((j & 1) * (16384 >> 4));
+        const uint64_t dK = dKmn0 + static_cast<uint64_t>((j % kRing) * (16384 >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dQ, dDS + 2 * k, dK + (2048 >> 4) * k, idesc_dq, (j > 0 || k > 0));
+        ptx::umma_commit(&kv_empty[j % kRing]);  // S_j / dP_j (other issuer) completed before ds_full(j) could complete
+        ptx::umma_commit(&dq_done[j & 1]);
+      }
+      ptx::umma_commit(all_done);
+    }
+    __syncwarp();
   } else {
+    const int g = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t sDS = ptx::smem_u32(smem + DqSmem::DS);
+    const uint32_t sDS = ptx::smem_u32(smem + DqSmem::DS) + g * 16384;
     const int t = qt * 128 + r;
     const bool valid = t < T;
     const long long stat_idx = (static_cast<long long>(b) * H + h) * T + t;
     const float neg_lse2 = valid ? -__ldg(lse + stat_idx) * kLog2e : 0.f;
     const float neg_delta8 = valid ? -__ldg(delta + stat_idx) * kScale : 0.f;
-    for (int j = 0; j < num_kv; ++j) {
-      ptx::mbar_wait(s_full, j & 1, 24);
+    const int r0 = qt * 128 + quarter * 32;
+    for (int j = g; j < num_kv; j += 2) {
+      const int use = j >> 1;
+      DQ_STAMP(0);
+      ptx::mbar_wait(&s_full[g], use & 1, 24);
       ptx::tc_fence_after();
+      DQ_STAMP(1);
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const int c0 = j * 64 + c * 32;      // first key column of the chunk
-        const int r0 = qt * 128 + quarter * 32;  // first query row of this warp
-        const uint32_t ta_s = tm_S + lane_off + c * 32, ta_dp = tm_dP + lane_off + c * 32;
+        const int c0 = j * 64 + c * 32;
+        const uint32_t ta_s = tmem_base + lane_off + g * 128 + c * 32, ta_dp = ta_s + 64;
         if (c0 + 31 <= r0) dq_chunk<kFull>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
         else if (c0 > r0 + 31) dq_chunk<kMasked>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
         else dq_chunk<kDiag>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
       }
-      if (j > 0) ptx::mbar_wait(dq_done, (j - 1) & 1, 25);  // previous dQ MMA has finished reading dS
+      DQ_STAMP(2);
+      if (use > 0) ptx::mbar_wait(&dq_done[g], (use - 1) & 1, 25);  // the dQ MMA of step j-2 has finished reading this dS buffer
+      DQ_STAMP(3);
       st_slab32(sDS, r, 0, pk);
       st_slab32(sDS, r, 1, pk + 16);
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(ds_full);
+      ptx::mbar_arrive(&ds_full[g]);
+      DQ_STAMP(4);
     }
-    ptx::mbar_wait(dq_done, (num_kv - 1) & 1, 26);
+#undef DQ_STAMP
+    ptx::mbar_wait(all_done, 0, 26);  // committed after the last MMA
     ptx::tc_fence_after();
-    __nv_bfloat16* o = dqkv + static_cast<long long>(b * T + t) * (3 * C) + h * HS;
+    // group g writes columns [32 g, 32 g + 32) of dQ
+    __nv_bfloat16* o = dqkv + static_cast<long long>(b * T + t) * (3 * C) + h * HS + g * 32;
+    uint32_t v[32];
+    ptx::tmem_ld32(tm_dQ + lane_off + g * 32, v);
+    ptx::tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 w;
+        w.x = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+        w.y = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+        w.z = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+        w.w = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+        reinterpret_cast<uint4*>(o)[q] = w;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+struct DkvSmem {
+  static constexpr int K = 0;          // 128 x 64
+  static constexpr int V = 16384;      // 128 x 64
+  static constexpr int QDO = 32768;    // kRing stages x (Q 64x64 | dO 64x64)
+  static constexpr int PT = QDO + kRing * 16384;  // 2 buffers x 128 x 64   P^T
+  static constexpr int DST = PT + 2 * 16384;      // 2 buffers x 128 x 64   dS^T
+  static constexpr int STAT = DST + 2 * 16384;    // 2 groups x 2 buffers x (-lse2[64] | -delta8[64]) fp32
+  static constexpr int BAR = STAT + 2048;
+  static constexpr int TOTAL = BAR + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                    const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
+                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, long long* trace) {
+  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
+#define DKV_STAMP(k) do { if (tr) trace[128 + n * 8 + (k)] = clock64(); } while (0)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DkvSmem::BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;                // [kRing]
+  uint64_t* qdo_empty = qdo_full + kRing;       // [kRing]
+  uint64_t* s_full = qdo_empty + kRing;         // [2]
+  uint64_t* pds_full = s_full + 2;              // [2]
+  uint64_t* pds_empty = pds_full + 2;           // [2]
+  uint64_t* all_done = pds_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
+  float* stat = reinterpret_cast<float*>(smem + DkvSmem::STAT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x;  // key tile; tile 0 is the heaviest and is scheduled first
+  const int b = blockIdx.y / H, h = blockIdx.y % H;
+  const int i0 = kt * 2;                // first 64-row query tile that can see this key tile
+  const int nq = (T + 63) / 64 - i0;    // >= 1
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQKV128);
+    ptx::prefetch_tmap(&tmQKV64);
+    ptx::prefetch_tmap(&tmDO64);
+    ptx::mbar_init(kv_full, 1);
+    for (int s = 0; s < kRing; ++s) {
+      ptx::mbar_init(&qdo_full[s], 1);
+      ptx::mbar_init(&qdo_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&pds_full[s], 128);
+      ptx::mbar_init(&pds_empty[s], 1);
+    }
+    ptx::mbar_init(all_done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;  // S^T_g at 128 g, dP^T_g at 128 g + 64
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(kv_full, 32768);
+      ptx::tma_load_2d(smem + DkvSmem::K, &tmQKV128, kv_full, C + h * HS, b * T + kt * 128);
+      ptx::tma_load_2d(smem + DkvSmem::V, &tmQKV128, kv_full, 2 * C + h * HS, b * T + kt * 128);
+      for (int n = 0; n < nq; ++n) {
+        const int st = n % kRing;
+        const uint32_t ph = (n / kRing) & 1;
+        ptx::mbar_wait(&qdo_empty[st], ph ^ 1, 30);
+        ptx::mbar_expect_tx(&qdo_full[st], 16384);
+        uint8_t* dst = smem + DkvSmem::QDO + st * 16384;
+        ptx::tma_load_2d(dst, &tmQKV64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
+        ptx::tma_load_2d(dst + 8192, &tmDO64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---- score MMAs: S^T_n = K Q_n^T, dP^T_n = V dO_n^T into TMEM buffer n & 1
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0, 0);
+      const uint64_t dK0 = desc_k(ptx::smem_u32(smem + DkvSmem::K), 0), dV0 = desc_k(ptx::smem_u32(smem + DkvSmem::V), 0);
+      const uint64_t dQDO0 = desc_k(ptx::smem_u32(smem + DkvSmem::QDO), 0);
+      ptx::mbar_wait(kv_full, 0, 31);
+      for (int n = 0; n < nq; ++n) {
+        ptx::mbar_wait(&qdo_full[n % kRing], (n / kRing) & 1, 32);
+        if (n >= 2) ptx::mbar_wait(&pds_full[n & 1], ((n - 2) >> 1) & 1, 33);  // group n&1 has consumed step n-2
+        ptx::tc_fence_after();
+        const uint64_t dQ = dQDO0 + static_cast<uint64_t>((n % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
+        const uint32_t tS = tmem_base + (n & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_ss(tS, dK0 + 2 * k, dQ + 2 * k, idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_ss(tS + 64, dV0 + 2 * k, dDO + 2 * k, idesc_s, k > 0);
+        ptx::umma_commit(&s_full[n & 1]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ---- accumulating MMAs: dV += P^T_n dO_n, dK += dS^T_n Q_n
+    if (lane == 0) {
+      constexpr uint32_t idesc_g = ptx::umma_idesc_bf16(128, 64, 0, 1);
+      const uint64_t dPT0 = desc_k(ptx::smem_u32(smem + DkvSmem::PT), 0), dDST0 = desc_k(ptx::smem_u32(smem + DkvSmem::DST), 0);
+      const uint64_t dQmn0 = desc_mn(ptx::smem_u32(smem + DkvSmem::QDO), 0);
+      for (int n = 0; n < nq; ++n) {
+        ptx::mbar_wait(&pds_full[n & 1], (n >> 1) & 1, 33);
+        ptx::tc_fence_after();
+        const uint64_t boff = static_cast<uint64_t>((n & 1) * (16384 >> 4));
+        const uint64_t dQ = dQmn0 + static_cast<uint64_t>((n % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dV, dPT0 + boff + 2 * k, dDO + (2048 >> 4) * k, idesc_g, (n > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dK, dDST0 + boff + 2 * k, dQ + (2048 >> 4) * k, idesc_g, (n > 0 || k > 0));
+        ptx::umma_commit(&qdo_empty[n % kRing]);
+        ptx::umma_commit(&pds_empty[n & 1]);
+      }
+      ptx::umma_commit(all_done);
+    }
+    __syncwarp();
+  } else {
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;      // key row inside the tile
+    const int tid = (warp - 2 - 4 * g) * 32 + lane;  // 0..127 within the group
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t sPT = ptx::smem_u32(smem + DkvSmem::PT) + g * 16384;
+    const uint32_t sDST = ptx::smem_u32(smem + DkvSmem::DST) + g * 16384;
+    const int kv_t = kt * 128 + r;
+    const bool valid = kv_t < T;
+    const long long stat_base = (static_cast<long long>(b) * H + h) * T;
+    const int r0 = kt * 128 + quarter * 32;
+    for (int n = g; n < nq; n += 2) {
+      const int use = n >> 1;
+      const int q0 = (i0 + n) * 64;
+      float* st_lse = stat + (g * 2 + (use & 1)) * 128;
+      {
+        const int qi = q0 + (tid & 63);
+        float v = 0.f;
+        if (qi < T) v = (tid < 64) ? -__ldg(lse + stat_base + qi) * kLog2e : -__ldg(delta + stat_base + qi) * kScale;
+        st_lse[tid] = v;
+      }
+      DKV_STAMP(0);
+      ptx::bar_sync(1 + g, 128);
+      ptx::mbar_wait(&s_full[g], use & 1, 34);
+      ptx::tc_fence_after();
+      DKV_STAMP(1);
+      uint32_t pk_p[32], pk_ds[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = q0 + c * 32;
+        const uint32_t ta_s = tmem_base + lane_off + g * 128 + c * 32, ta_dp = ta_s + 64;
+        const float* l2 = st_lse + c * 32;
+        const float* d8 = st_lse + 64 + c * 32;
+        if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
+        else if (c0 + 31 < r0 || c0 >= T) dkv_chunk<kMasked>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
+        else dkv_chunk<kDiag>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
+      }
+      DKV_STAMP(2);
+      if (use > 0) ptx::mbar_wait(&pds_empty[g], (use - 1) & 1, 35);
+      DKV_STAMP(3);
+      st_slab32(sPT, r, 0, pk_p);
+      st_slab32(sPT, r, 1, pk_p + 16);
+      st_slab32(sDST, r, 0, pk_ds);
+      st_slab32(sDST, r, 1, pk_ds + 16);
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&pds_full[g]);
+      DKV_STAMP(4);
+    }
+#undef DKV_STAMP
+    ptx::mbar_wait(all_done, 0, 36);  // committed after the last MMA
+    ptx::tc_fence_after();
+    // group 0 writes dV, group 1 writes dK
+    __nv_bfloat16* o = dqkv + static_cast<long long>(b * T + kv_t) * (3 * C) + (g == 0 ? 2 * C : C) + h * HS;
+    const uint32_t tm = g == 0 ? tm_dV : tm_dK;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      ptx::tmem_ld32(tm_dQ + lane_off + c * 32, v);
+      ptx::tmem_ld32(tm + lane_off + c * 32, v);
       ptx::tmem_ld_wait();
       if (valid) {
 #pragma unroll
@@ -546,186 +863,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
-}
-
-// ======================================================================================================
-// backward: dK, dV
-// ======================================================================================================
-struct DkvSmem {
-  static constexpr int K = 0;        // 128 x 64
-  static constexpr int V = 16384;    // 128 x 64
-  static constexpr int QDO = 32768;  // 2 stages x (Q 64x64 | dO 64x64)
-  static constexpr int PT = 65536;   // 128 x 64  P^T
-  static constexpr int DST = 81920;  // 128 x 64  dS^T
-  static constexpr int STAT = 98304; // 2 stages x (lse2[64] | delta[64]) fp32
-  static constexpr int BAR = 99328;
-  static constexpr int TOTAL = BAR + 128 + 1024;
-};
-
-__global__ void __launch_bounds__(kThreads, 2)
-attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
-                    const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
-                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DkvSmem::BAR);
-  uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;   // [2]
-  uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* pds_full = bars + 6;
-  uint64_t* pds_empty = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* stat = reinterpret_cast<float*>(smem + DkvSmem::STAT);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x;  // key tile; tile 0 is the heaviest and is scheduled first
-  const int b = blockIdx.y / H, h = blockIdx.y % H;
-  const int i0 = kt * 2;                // first 64-row query tile that can see this key tile
-  const int nq = (T + 63) / 64 - i0;    // >= 1
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmQKV128);
-    ptx::prefetch_tmap(&tmQKV64);
-    ptx::prefetch_tmap(&tmDO64);
-    ptx::mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&qdo_full[s], 1);
-      ptx::mbar_init(&qdo_empty[s], 1);
-    }
-    ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(pds_full, 128);
-    ptx::mbar_init(pds_empty, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 256);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 64, tm_dV = tmem_base + 128, tm_dK = tmem_base + 192;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      ptx::mbar_expect_tx(kv_full, 32768);
-      ptx::tma_load_2d(smem + DkvSmem::K, &tmQKV128, kv_full, C + h * HS, b * T + kt * 128);
-      ptx::tma_load_2d(smem + DkvSmem::V, &tmQKV128, kv_full, 2 * C + h * HS, b * T + kt * 128);
-      for (int n = 0; n < nq; ++n) {
-        const int st = n & 1;
-        const uint32_t ph = (n >> 1) & 1;
-        ptx::mbar_wait(&qdo_empty[st], ph ^ 1, 30);
-        ptx::mbar_expect_tx(&qdo_full[st], 16384);
-        uint8_t* dst = smem + DkvSmem::QDO + st * 16384;
-        ptx::tma_load_2d(dst, &tmQKV64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
-        ptx::tma_load_2d(dst + 8192, &tmDO64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_g = ptx::umma_idesc_bf16(128, 64, 0, 1);
-      const uint32_t sK = ptx::smem_u32(smem + DkvSmem::K), sV = ptx::smem_u32(smem + DkvSmem::V);
-      const uint32_t sPT = ptx::smem_u32(smem + DkvSmem::PT), sDST = ptx::smem_u32(smem + DkvSmem::DST);
-      ptx::mbar_wait(kv_full, 0, 31);
-      for (int n = 0; n < nq; ++n) {
-        const int st = n & 1;
-        const uint32_t ph = (n >> 1) & 1;
-        const uint32_t sQ = ptx::smem_u32(smem + DkvSmem::QDO + st * 16384), sDO = sQ + 8192;
-        ptx::mbar_wait(&qdo_full[st], ph, 32);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_S, desc_k(sK, k), desc_k(sQ, k), idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dP, desc_k(sV, k), desc_k(sDO, k), idesc_s, k > 0);
-        ptx::umma_commit(s_full);
-        ptx::mbar_wait(pds_full, n & 1, 33);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dV, desc_k(sPT, k), desc_mn(sDO, k), idesc_g, (n > 0 || k > 0));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dK, desc_k(sDST, k), desc_mn(sQ, k), idesc_g, (n > 0 || k > 0));
-        ptx::umma_commit(&qdo_empty[st]);
-        ptx::umma_commit(pds_empty);
-      }
-    }
-    __syncwarp();
-  } else {
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // key row inside the tile
-    const int tid = threadIdx.x - 64;   // 0..127 within the compute group
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t sPT = ptx::smem_u32(smem + DkvSmem::PT), sDST = ptx::smem_u32(smem + DkvSmem::DST);
-    const int kv_t = kt * 128 + r;
-    const bool valid = kv_t < T;
-    const long long stat_base = (static_cast<long long>(b) * H + h) * T;
-    for (int n = 0; n < nq; ++n) {
-      const int q0 = (i0 + n) * 64;
-      float* st_lse = stat + (n & 1) * 128;
-      {
-        const int qi = q0 + (tid & 63);
-        float v = 0.f;
-        if (qi < T) v = (tid < 64) ? -__ldg(lse + stat_base + qi) * kLog2e : -__ldg(delta + stat_base + qi) * kScale;
-        st_lse[tid] = v;
-      }
-      ptx::bar_sync(1, 128);
-      ptx::mbar_wait(s_full, n & 1, 34);
-      ptx::tc_fence_after();
-      uint32_t pk_p[32], pk_ds[32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int c0 = q0 + c * 32;                 // first query column of the chunk
-        const int r0 = kt * 128 + quarter * 32;     // first key row of this warp
-        const uint32_t ta_s = tm_S + lane_off + c * 32, ta_dp = tm_dP + lane_off + c * 32;
-        const float* l2 = st_lse + c * 32;
-        const float* d8 = st_lse + 64 + c * 32;
-        if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
-        else if (c0 + 31 < r0 || c0 >= T) dkv_chunk<kMasked>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
-        else dkv_chunk<kDiag>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
-      }
-      if (n > 0) ptx::mbar_wait(pds_empty, (n - 1) & 1, 35);
-      st_slab32(sPT, r, 0, pk_p);
-      st_slab32(sPT, r, 1, pk_p + 16);
-      st_slab32(sDST, r, 0, pk_ds);
-      st_slab32(sDST, r, 1, pk_ds + 16);
-      ptx::fence_proxy_async_smem();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(pds_full);
-    }
-    ptx::mbar_wait(pds_empty, (nq - 1) & 1, 36);
-    ptx::tc_fence_after();
-    __nv_bfloat16* ok = dqkv + static_cast<long long>(b * T + kv_t) * (3 * C) + C + h * HS;
-    __nv_bfloat16* ov = ok + C;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* o = which == 0 ? ov : ok;
-      const uint32_t tm = which == 0 ? tm_dV : tm_dK;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tm + lane_off + c * 32, v);
-        ptx::tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 w;
-            w.x = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-            w.y = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-            w.z = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-            w.w = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-            reinterpret_cast<uint4*>(o)[c * 4 + q] = w;
-          }
-        }
-      }
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 template <typename K>
@@ -749,9 +887,9 @@ int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, cudaSt
   if (rc) return rc;
   ABCGPT_CHECK_ARG(qkv && out && lse, "attn_fwd: null pointer");
   const int C = H * HS;
-  CUtensorMap tm;
-  rc = encode_tmap_2d(&tm, qkv, 2, 3ull * C, static_cast<uint64_t>(B) * T, 3ull * C * 2, 64, 128, true);
-  if (rc) return rc;
+  CUtensorMap tmQ, tmKV;
+  if ((rc = encode_tmap_2d(&tmQ, qkv, 2, 3ull * C, static_cast<uint64_t>(B) * T, 3ull * C * 2, 64, 128, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmKV, qkv, 2, 3ull * C, static_cast<uint64_t>(B) * T, 3ull * C * 2, 64, 64, true))) return rc;
   static bool done = false;
   if (!done) {
     rc = set_smem(attn_fwd_kernel, FwdSmem::TOTAL);
@@ -759,7 +897,8 @@ int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, cudaSt
     done = true;
   }
   dim3 grid((T + 127) / 128, B * H);
-  attn_fwd_kernel<<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), lse, T, H, C);
+  attn_fwd_kernel<<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse, T, H, C,
+                                                              g_attn_trace);
   return launch_status("attn_fwd_kernel");
 }
 
@@ -788,11 +927,11 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
     if ((rc = launch_status("attn_delta_kernel"))) return rc;
   }
   dim3 grid((T + 127) / 128, B * H);
-  attn_bwd_dkv_kernel<<<grid, kThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta,
-                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, C);
+  attn_bwd_dkv_kernel<<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, C, g_attn_trace);
   if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
-  attn_bwd_dq_kernel<<<grid, kThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta,
-                                                               reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, C);
+  attn_bwd_dq_kernel<<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta,
+                                                               reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, C, g_attn_trace);
   return launch_status("attn_bwd_dq_kernel");
 }
 

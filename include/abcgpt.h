@@ -124,6 +124,9 @@ int abcgpt_argmax(const void* logits, int64_t ldl, int V, int64_t* out, int64_t 
 /* Debug aid: device pointer to 8 uint64 cycle counters accumulated by subsequent GEMM launches (NULL disables):
  * [0] producer empty-wait [1] MMA full-wait [2] MMA tmem-empty wait [3] epilogue tmem-full wait [5] CTA total. */
 int abcgpt_debug_gemm_stats(void* device_counters);
+/* Debug aid: device pointer to int64[num_kv_tiles * 8]; one CTA of the next attention forward launches stamps clock64
+ * at its phase boundaries (NULL disables). */
+int abcgpt_debug_attn_trace(void* device_stamps);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,44 @@
+"""Phase timeline of one attention-forward CTA (the 8-tile row block of head 0): cycles between stamps."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ai_music_generation_b200 import _C, ops
+B, T, H = 32, 1024, 12
+C = H * 64
+qkv = torch.randn(B * T, 3 * C, device="cuda").bfloat16()
+o = torch.empty(B * T, C, device="cuda", dtype=torch.bfloat16)
+lse = torch.empty(B, H, T, device="cuda")
+for _ in range(3):
+    ops.attn_fwd(qkv, o, lse, B, T, H)
+tr = torch.zeros(16 * 8, device="cuda", dtype=torch.int64)
+_C.lib().abcgpt_debug_attn_trace(tr.data_ptr())
+ops.attn_fwd(qkv, o, lse, B, T, H)
+torch.cuda.synchronize()
+_C.lib().abcgpt_debug_attn_trace(0)
+
+n = 16
+print("tile: wait_S  compute  wait_Pbuf  store+arrive | total")
+t = tr.view(-1, 8).cpu()
+for j in range(n):
+    r = t[j]
+    print(j, (r[1] - r[0]).item(), (r[2] - r[1]).item(), (r[3] - r[2]).item(), (r[4] - r[3]).item(), "|", (r[4] - r[0]).item())
+print("whole CTA:", (t[n - 1][4] - t[0][0]).item(), "cycles")
+
+# backward kernels: dq stamps at [0,128), dkv at [128,256)
+do = torch.randn(B * T, C, device="cuda").bfloat16()
+dqkv = torch.empty(B * T, 3 * C, device="cuda", dtype=torch.bfloat16)
+delta = torch.empty(B, H, T, device="cuda")
+for _ in range(2):
+    ops.attn_bwd(qkv, o, do, lse, delta, dqkv, B, T, H)
+tr2 = torch.zeros(256, device="cuda", dtype=torch.int64)
+_C.lib().abcgpt_debug_attn_trace(tr2.data_ptr())
+ops.attn_bwd(qkv, o, do, lse, delta, dqkv, B, T, H)
+torch.cuda.synchronize()
+_C.lib().abcgpt_debug_attn_trace(0)
+for name, base in (("dq", 0), ("dkv", 128)):
+    t = tr2[base:base + 128].view(16, 8).cpu()
+    print(name, "step: wait_S  compute  wait_prev_mma  store+arrive | total")
+    for j in range(16):
+        r = t[j]
+        print(j, (r[1] - r[0]).item(), (r[2] - r[1]).item(), (r[3] - r[2]).item(), (r[4] - r[3]).item(), "|", (r[4] - r[0]).item())
+    print(name, "whole:", (t[15][4] - t[0][0]).item())

@@ -144,13 +144,20 @@ def _attn_ref(qkv, B, T, H):
     return o, lse
 
 
-def case_attn(name, B, T, H, bwd, timing=True):
+def case_attn(name, B, T, H, bwd, timing=True, spike=False):
     import torch
     from ai_music_generation_b200 import ops
     torch.manual_seed(0)
     dev = "cuda"
     C = H * 64
-    qkv = torch.randn(B * T, 3 * C, device=dev).bfloat16()
+    qkv = torch.randn(B * T, 3 * C, device=dev)
+    if spike:
+        # scores jump by ~2^100 after the first 64 keys: exercises the lazy-rescale path of the forward kernel
+        sign = torch.where(torch.arange(C, device=dev) % 2 == 0, 1.0, -1.0)
+        qkv[:, :C] = 3.0 * sign
+        v3 = qkv.view(B, T, 3 * C)
+        v3[:, 64:, C:2 * C] = 3.0 * sign + 0.05 * torch.randn(B, T - 64, C, device=dev)
+    qkv = qkv.bfloat16()
     out = torch.zeros(B * T, C, device=dev, dtype=torch.bfloat16)
     lse = torch.zeros(B, H, T, device=dev)
     res = {"case": name}
@@ -358,6 +365,7 @@ def build_cases():
     cases["attn_t1024"] = lambda: case_attn("attn_t1024", 2, 1024, 2, True, timing=False)
     cases["attn_t32"] = lambda: case_attn("attn_t32", 3, 32, 2, True, timing=False)
     cases["attn_t200"] = lambda: case_attn("attn_t200", 2, 200, 2, True, timing=False)
+    cases["attn_spike"] = lambda: case_attn("attn_spike", 2, 320, 2, True, timing=False, spike=True)
     cases["attn_perf_cfg2"] = lambda: case_attn("attn_perf_cfg2", 64, 256, 6, True)
     cases["attn_perf_cfg3"] = lambda: case_attn("attn_perf_cfg3", 32, 1024, 12, True)
     # --- memory-bound kernels
