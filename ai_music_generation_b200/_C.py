@@ -32,7 +32,7 @@ _SIGNATURES = {
     "abcgpt_ce_fwd": (c_int, [_P, c_int64, _P, _P, c_int, c_int, _P]),
     "abcgpt_ce_finalize": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "abcgpt_ce_bwd": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, _P]),
-    "abcgpt_sumsq": (c_int, [_P, c_int64, _P, _P]),
+    "abcgpt_sumsq": (c_int, [_P, c_int64, _P, _P, _P]),
     "abcgpt_adamw": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, _P,
                              c_float, _P]),
     "abcgpt_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),

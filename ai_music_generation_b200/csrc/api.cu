@@ -60,7 +60,9 @@ int abcgpt_ce_bwd(const void* logits, int64_t ldl, const int64_t* targets, const
   return ce_bwd(logits, ldl, targets, loss_sum_count, grad_loss, dlogits, M, V, S(stream));
 }
 
-int abcgpt_sumsq(const float* g, int64_t n, float* out, void* stream) { return sumsq(g, n, out, S(stream)); }
+int abcgpt_sumsq(const float* g, int64_t n, float* out, float* workspace, void* stream) {
+  return sumsq(g, n, out, workspace, S(stream));
+}
 int abcgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, const float* sumsq_ptr, float max_norm,
                  void* stream) {

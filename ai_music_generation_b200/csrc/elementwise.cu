@@ -188,7 +188,10 @@ ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl, const int
 }
 
 // ---- gradient norm, clip + AdamW (train.py:350-354; torch.optim.AdamW single-tensor formulas) -----------------
-__global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// Deterministic two-stage reduction (fixed grid, fixed order): every data-parallel rank must derive the SAME clip
+// coefficient from the same all-reduced gradients, or the replicas drift apart bit by bit.
+constexpr int kSumsqBlocks = 1024;
+__global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
   __shared__ float sh[16];
   float s = 0.f;
   const long long n4 = n >> 2;
@@ -208,7 +211,19 @@ __global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g,
   if (threadIdx.x < 32) {
     s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
     s = warp_sum(s);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(1024) sumsq_final_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = threadIdx.x < nparts ? partial[threadIdx.x] : 0.f;
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = sh[threadIdx.x];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[0] += s;
   }
 }
 
@@ -397,11 +412,14 @@ int ce_bwd(const void* logits, long long ldl, const int64_t* targets, const floa
   return launch_status("ce_bwd_kernel");
 }
 
-int sumsq(const float* g, long long n, float* out, cudaStream_t stream) {
-  ABCGPT_CHECK_ARG(g && out && n > 0, "sumsq: bad arguments");
+int sumsq(const float* g, long long n, float* out, float* workspace, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(g && out && workspace && n > 0, "sumsq: bad arguments");
   ABCGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: pointer must be 16-byte aligned");
-  sumsq_kernel<<<grid_for(n / 4 + 1, 512, 4), 512, 0, stream>>>(g, n, out);
-  return launch_status("sumsq_kernel");
+  sumsq_kernel<<<kSumsqBlocks, 512, 0, stream>>>(g, n, workspace);
+  int rc = launch_status("sumsq_kernel");
+  if (rc) return rc;
+  sumsq_final_kernel<<<1, 1024, 0, stream>>>(workspace, kSumsqBlocks, out);
+  return launch_status("sumsq_final_kernel");
 }
 
 int adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,

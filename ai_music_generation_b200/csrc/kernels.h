@@ -33,7 +33,7 @@ int ce_finalize(const float* row_loss, const int64_t* targets, int M, float* los
 int ce_bwd(const void* logits, long long ldl, const int64_t* targets, const float* loss_sum_count,
            const float* grad_loss, void* dlogits, int M, int V, cudaStream_t stream);
 
-int sumsq(const float* g, long long n, float* out, cudaStream_t stream);
+int sumsq(const float* g, long long n, float* out, float* workspace, cudaStream_t stream);
 int adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
           float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,
           cudaStream_t stream);

@@ -141,8 +141,14 @@ def ce_bwd(logits, targets, sum_count, grad_loss, dlogits, V):
           grad_loss.data_ptr(), dlogits.data_ptr(), M, V, _stream())
 
 
+_SUMSQ_WS = {}
+
+
 def sumsq(g, out):
-    _call("sumsq", 1, (g.numel(),), _C.lib().abcgpt_sumsq, g.data_ptr(), g.numel(), out.data_ptr(), _stream())
+    ws = _SUMSQ_WS.get(g.device)
+    if ws is None:
+        ws = _SUMSQ_WS[g.device] = torch.empty(1024, device=g.device, dtype=torch.float32)
+    _call("sumsq", 2, (g.numel(),), _C.lib().abcgpt_sumsq, g.data_ptr(), g.numel(), out.data_ptr(), ws.data_ptr(), _stream())
 
 
 def adamw(p, g, m, v, shadow, *, lr, beta1, beta2, eps, weight_decay, step, sumsq=None, max_norm=0.0):

@@ -99,13 +99,14 @@ int abcgpt_ce_bwd(const void* logits, int64_t ldl, const int64_t* targets, const
 
 /*
  * Gradient norm + clipping + AdamW over flat fp32 arenas         train.py:350-354, model.py:263-287
- * sumsq: out[0] += sum(g^2) (caller zeroes out[0]).
+ * sumsq: out[0] += sum(g^2) (caller zeroes out[0]); deterministic two-stage reduction through `workspace`
+ *        (>= 1024 floats) so that every data-parallel rank derives the same clip coefficient.
  * adamw: torch.optim.AdamW semantics (decoupled decay p *= 1 - lr*wd; eps outside the bias-corrected sqrt),
  *        `step` is the 1-based step count.  If sumsq != NULL the gradient is first scaled by
  *        min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))  (clip_grad_norm_).  If shadow_bf16 != NULL the updated
  *        parameter is also written there rounded to bf16 (the GEMM operand copy for the next step).
  */
-int abcgpt_sumsq(const float* g, int64_t n, float* out, void* stream);
+int abcgpt_sumsq(const float* g, int64_t n, float* out, float* workspace, void* stream);
 int abcgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,
                  void* stream);
