@@ -55,6 +55,11 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t slab_addr, int k16) {
 }
 
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float2 f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 // Per-chunk mask classes (a chunk = 32 consecutive score columns seen by one warp = 32 consecutive rows).  Row and
@@ -151,7 +156,7 @@ __device__ __forceinline__ void dq_chunk(uint32_t taddr_s, uint32_t taddr_dp, in
 // backward (dK/dV kernel): P^T and dS^T for one chunk; statistics are per COLUMN (query), read from shared memory.
 // MODE kDiag here is the general path: keep iff (q >= kv) && (q < T).
 template <int MODE>
-__device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, const float* st_lse2, const float* st_delta8,
+__device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, uint32_t st_lse2, uint32_t st_delta8,
                                           int q_base, int kv_t, int T, uint32_t* pk_p, uint32_t* pk_ds) {
   if (MODE == kMasked) {
 #pragma unroll
@@ -165,8 +170,8 @@ __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, c
   const float2 sl = make_float2(kSl2, kSl2), sc = make_float2(kScale, kScale);
 #pragma unroll
   for (int i4 = 0; i4 < 8; ++i4) {
-    const float4 l4 = reinterpret_cast<const float4*>(st_lse2)[i4];     // already negated: -lse*log2e
-    const float4 d4 = reinterpret_cast<const float4*>(st_delta8)[i4];   // already negated: -delta*scale
+    const float4 l4 = lds128(st_lse2 + 16 * i4);     // already negated: -lse*log2e   (ld.shared, broadcast)
+    const float4 d4 = lds128(st_delta8 + 16 * i4);   // already negated: -delta*scale
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int i = 2 * i4 + h;  // pair index: columns 2i, 2i+1
@@ -483,6 +488,7 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
 // into dS, the tensor core already produces S/dP of step j+1 for group 1, and the accumulating MMAs (dQ, or dV and dK)
 // of finished steps interleave in between.  Without this, every step serialises "MMA -> exp/dS -> MMA" (measured:
 // ~1400 of ~2700 cycles per step spent waiting for the score MMAs).
+constexpr int kSBuf = 3;          // S/dP score buffers in TMEM: two are being consumed by the two groups, one is being produced
 constexpr int kRing = 6;          // K/V (dQ kernel) or Q/dO (dK/dV kernel) tiles in flight: TMA latency >> one step
 constexpr int kBwdThreads = 352;  // warp 0 TMA, warp 1 score MMAs, warps 2..5 group 0, warps 6..9 group 1, warp 10 accumulating MMAs
 
@@ -507,8 +513,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   uint64_t* qdo_full = bars + 0;
   uint64_t* kv_full = bars + 1;                 // [kRing]
   uint64_t* kv_empty = kv_full + kRing;         // [kRing]
-  uint64_t* s_full = kv_empty + kRing;          // [2]
-  uint64_t* ds_full = s_full + 2;               // [2]
+  uint64_t* s_full = kv_empty + kRing;          // [kSBuf]
+  uint64_t* s_free = s_full + kSBuf;            // [kSBuf]
+  uint64_t* ds_full = s_free + kSBuf;           // [2]
   uint64_t* dq_done = ds_full + 2;              // [2]
   uint64_t* all_done = dq_done + 2;  // dedicated: a parity wait is only meaningful to a thread that followed every phase
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
@@ -529,8 +536,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
       ptx::mbar_init(&kv_full[s], 1);
       ptx::mbar_init(&kv_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kSBuf; ++s) {
       ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&s_free[s], 128);
+    }
+    for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&ds_full[s], 128);
       ptx::mbar_init(&dq_done[s], 1);
     }
@@ -545,7 +555,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_dQ = tmem_base + 256;  // S_g at 128 g, dP_g at 128 g + 64
+  const uint32_t tm_dQ = tmem_base + 128 * kSBuf;  // score buffer b: S at 128 b, dP at 128 b + 64
 
   if (warp == 0) {
     if (lane == 0) {
@@ -573,15 +583,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
       ptx::mbar_wait(qdo_full, 0, 21);
       for (int j = 0; j < num_kv; ++j) {
         ptx::mbar_wait(&kv_full[j % kRing], (j / kRing) & 1, 22);
-        if (j >= 2) ptx::mbar_wait(&ds_full[j & 1], ((j - 2) >> 1) & 1, 23);  // group j&1 has consumed S/dP of step j-2
+        if (j >= kSBuf) ptx::mbar_wait(&s_free[j % kSBuf], ((j / kSBuf) - 1) & 1, 23);  // step j-3 has left this buffer
         ptx::tc_fence_after();
         const uint64_t dK = dKV0 + static_cast<uint64_t>((j % kRing) * (16384 >> 4)), dV = dK + (8192 >> 4);
-        const uint32_t tS = tmem_base + (j & 1) * 128;
+        const uint32_t tS = tmem_base + (j % kSBuf) * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::umma_ss(tS, dQ0 + 2 * k, dK + 2 * k, idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::umma_ss(tS + 64, dDO0 + 2 * k, dV + 2 * k, idesc_s, k > 0);
-        ptx::umma_commit(&s_full[j & 1]);
+        ptx::umma_commit(&s_full[j % kSBuf]);
       }
     }
     __syncwarp();
@@ -619,18 +629,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     for (int j = g; j < num_kv; j += 2) {
       const int use = j >> 1;
       DQ_STAMP(0);
-      ptx::mbar_wait(&s_full[g], use & 1, 24);
+      ptx::mbar_wait(&s_full[j % kSBuf], (j / kSBuf) & 1, 24);
       ptx::tc_fence_after();
       DQ_STAMP(1);
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int c0 = j * 64 + c * 32;
-        const uint32_t ta_s = tmem_base + lane_off + g * 128 + c * 32, ta_dp = ta_s + 64;
+        const uint32_t ta_s = tmem_base + lane_off + (j % kSBuf) * 128 + c * 32, ta_dp = ta_s + 64;
         if (c0 + 31 <= r0) dq_chunk<kFull>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
         else if (c0 > r0 + 31) dq_chunk<kMasked>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
         else dq_chunk<kDiag>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
       }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s_free[j % kSBuf]);  // both score tiles of this step are in registers
       DQ_STAMP(2);
       if (use > 0) ptx::mbar_wait(&dq_done[g], (use - 1) & 1, 25);  // the dQ MMA of step j-2 has finished reading this dS buffer
       DQ_STAMP(3);
@@ -689,8 +701,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   uint64_t* kv_full = bars + 0;
   uint64_t* qdo_full = bars + 1;                // [kRing]
   uint64_t* qdo_empty = qdo_full + kRing;       // [kRing]
-  uint64_t* s_full = qdo_empty + kRing;         // [2]
-  uint64_t* pds_full = s_full + 2;              // [2]
+  uint64_t* s_full = qdo_empty + kRing;         // [kSBuf]
+  uint64_t* s_free = s_full + kSBuf;            // [kSBuf]
+  uint64_t* pds_full = s_free + kSBuf;          // [2]
   uint64_t* pds_empty = pds_full + 2;           // [2]
   uint64_t* all_done = pds_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
@@ -711,8 +724,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       ptx::mbar_init(&qdo_full[s], 1);
       ptx::mbar_init(&qdo_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kSBuf; ++s) {
       ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&s_free[s], 128);
+    }
+    for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&pds_full[s], 128);
       ptx::mbar_init(&pds_empty[s], 1);
     }
@@ -727,7 +743,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;  // S^T_g at 128 g, dP^T_g at 128 g + 64
+  const uint32_t tm_dV = tmem_base + 128 * kSBuf, tm_dK = tm_dV + 64;  // score buffer b: S^T at 128 b, dP^T at 128 b + 64
 
   if (warp == 0) {
     if (lane == 0) {
@@ -754,15 +770,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       ptx::mbar_wait(kv_full, 0, 31);
       for (int n = 0; n < nq; ++n) {
         ptx::mbar_wait(&qdo_full[n % kRing], (n / kRing) & 1, 32);
-        if (n >= 2) ptx::mbar_wait(&pds_full[n & 1], ((n - 2) >> 1) & 1, 33);  // group n&1 has consumed step n-2
+        if (n >= kSBuf) ptx::mbar_wait(&s_free[n % kSBuf], ((n / kSBuf) - 1) & 1, 33);  // step n-3 has left this buffer
         ptx::tc_fence_after();
         const uint64_t dQ = dQDO0 + static_cast<uint64_t>((n % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
-        const uint32_t tS = tmem_base + (n & 1) * 128;
+        const uint32_t tS = tmem_base + (n % kSBuf) * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::umma_ss(tS, dK0 + 2 * k, dQ + 2 * k, idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::umma_ss(tS + 64, dV0 + 2 * k, dDO + 2 * k, idesc_s, k > 0);
-        ptx::umma_commit(&s_full[n & 1]);
+        ptx::umma_commit(&s_full[n % kSBuf]);
       }
     }
     __syncwarp();
@@ -811,20 +827,21 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       }
       DKV_STAMP(0);
       ptx::bar_sync(1 + g, 128);
-      ptx::mbar_wait(&s_full[g], use & 1, 34);
+      ptx::mbar_wait(&s_full[n % kSBuf], (n / kSBuf) & 1, 34);
       ptx::tc_fence_after();
       DKV_STAMP(1);
       uint32_t pk_p[32], pk_ds[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int c0 = q0 + c * 32;
-        const uint32_t ta_s = tmem_base + lane_off + g * 128 + c * 32, ta_dp = ta_s + 64;
-        const float* l2 = st_lse + c * 32;
-        const float* d8 = st_lse + 64 + c * 32;
+        const uint32_t ta_s = tmem_base + lane_off + (n % kSBuf) * 128 + c * 32, ta_dp = ta_s + 64;
+        const uint32_t l2 = ptx::smem_u32(st_lse) + c * 128, d8 = l2 + 256;
         if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
         else if (c0 + 31 < r0 || c0 >= T) dkv_chunk<kMasked>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
         else dkv_chunk<kDiag>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
       }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s_free[n % kSBuf]);
       DKV_STAMP(2);
       if (use > 0) ptx::mbar_wait(&pds_empty[g], (use - 1) & 1, 35);
       DKV_STAMP(3);
