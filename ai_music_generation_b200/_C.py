@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import re
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libabcgpt.so")
@@ -22,13 +22,13 @@ _SIGNATURES = {
     "abcgpt_version": (c_int, []),
     "abcgpt_last_error": (c_char_p, []),
     "abcgpt_gemm_bf16": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P,
-                                 c_int64, _P, c_int64, _P, c_int, c_int, _P]),
-    "abcgpt_embed_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
-    "abcgpt_embed_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+                                 c_int64, _P, c_int64, _P, c_int, c_int, c_float, c_uint32, _P]),
+    "abcgpt_embed_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_uint32, _P]),
+    "abcgpt_embed_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_uint32, _P]),
     "abcgpt_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
-    "abcgpt_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
-    "abcgpt_attn_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
-    "abcgpt_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "abcgpt_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_uint32, _P]),
+    "abcgpt_attn_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, c_uint32, _P]),
+    "abcgpt_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_uint32, _P]),
     "abcgpt_ce_fwd": (c_int, [_P, c_int64, _P, _P, c_int, c_int, _P]),
     "abcgpt_ce_finalize": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "abcgpt_ce_bwd": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, _P]),

@@ -15,18 +15,19 @@ const char* abcgpt_last_error(void) { return last_error_buf(); }
 
 int abcgpt_gemm_bf16(const void* a, int a_mn_major, int64_t lda, const void* b, int b_mn_major, int64_t ldb, int M,
                      int N, int K, int epilogue, void* c, int64_t ldc, void* c2, int64_t ldc2, const void* aux,
-                     int64_t ldaux, const float* bias, int tile_n, int splits, void* stream) {
+                     int64_t ldaux, const float* bias, int tile_n, int splits, float dropout_p, uint32_t dropout_key,
+                     void* stream) {
   return gemm_bf16(a, a_mn_major, lda, b, b_mn_major, ldb, M, N, K, epilogue, c, ldc, c2, ldc2, aux, ldaux, bias,
-                   tile_n, splits, S(stream));
+                   tile_n, splits, dropout_p, dropout_key, S(stream));
 }
 
 int abcgpt_embed_fwd(const int64_t* idx, const float* wte, const float* wpe, float* x, int M, int T, int C, int V,
-                     void* stream) {
-  return embed_fwd(idx, wte, wpe, x, M, T, C, V, S(stream));
+                     float dropout_p, uint32_t dropout_key, void* stream) {
+  return embed_fwd(idx, wte, wpe, x, M, T, C, V, dropout_p, dropout_key, S(stream));
 }
 int abcgpt_embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int M, int T, int C, int V,
-                     void* stream) {
-  return embed_bwd(idx, dx, dwte, dwpe, M, T, C, V, S(stream));
+                     float dropout_p, uint32_t dropout_key, void* stream) {
+  return embed_bwd(idx, dx, dwte, dwpe, M, T, C, V, dropout_p, dropout_key, S(stream));
 }
 
 int abcgpt_layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* y_f32,
@@ -35,16 +36,18 @@ int abcgpt_layernorm_fwd(const float* x, const float* weight, const float* bias,
 }
 int abcgpt_layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean,
                          const float* rstd, const float* dresid_in, float* dx_out, void* dx_bf16, float* dweight,
-                         float* dbias, int M, int C, void* stream) {
-  return layernorm_bwd(dy_bf16, x, weight, mean, rstd, dresid_in, dx_out, dx_bf16, dweight, dbias, M, C, S(stream));
+                         float* dbias, int M, int C, float dropout_p, uint32_t dropout_key, void* stream) {
+  return layernorm_bwd(dy_bf16, x, weight, mean, rstd, dresid_in, dx_out, dx_bf16, dweight, dbias, M, C, dropout_p,
+                       dropout_key, S(stream));
 }
 
-int abcgpt_attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, void* stream) {
-  return attn_fwd(qkv, out, lse, B, T, H, S(stream));
+int abcgpt_attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float dropout_p, uint32_t dropout_key,
+                    void* stream) {
+  return attn_fwd(qkv, out, lse, B, T, H, dropout_p, dropout_key, S(stream));
 }
 int abcgpt_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
-                    int B, int T, int H, void* stream) {
-  return attn_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, S(stream));
+                    int B, int T, int H, float dropout_p, uint32_t dropout_key, void* stream) {
+  return attn_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, dropout_p, dropout_key, S(stream));
 }
 
 int abcgpt_ce_fwd(const void* logits, int64_t ldl, const int64_t* targets, float* row_loss, int M, int V,

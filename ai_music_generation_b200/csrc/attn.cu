@@ -11,6 +11,7 @@
 //                         dK += dS^T Q (TMEM acc).  Two kernels instead of atomics on dQ: deterministic gradients.
 // Two CTAs are co-resident per SM so that one CTA's softmax (MUFU-bound) overlaps the other's MMAs.
 #include "common.h"
+#include "dropout.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -125,9 +126,9 @@ __device__ __forceinline__ float fwd_chunk_exp(uint32_t taddr, int lane, float n
 }
 
 // backward (dQ kernel): dS = P * (dP*scale - delta*scale) for one chunk; row statistics are per thread
-template <int MODE>
+template <int MODE, bool DROP>
 __device__ __forceinline__ void dq_chunk(uint32_t taddr_s, uint32_t taddr_dp, int lane, float neg_lse2, float neg_delta8,
-                                         uint32_t* pk) {
+                                         uint32_t* pk, const DropCfg& dcfg, uint32_t drop_rk, int kv0) {
   if (MODE == kMasked) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = 0u;
@@ -143,7 +144,13 @@ __device__ __forceinline__ void dq_chunk(uint32_t taddr_s, uint32_t taddr_dp, in
   for (int i = 0; i < 16; ++i) {
     const float2 t = __ffma2_rn(f2(s[2 * i], s[2 * i + 1]), sl, nl);
     const float2 p = make_float2(ex2(t.x), ex2(t.y));
-    const float2 u = __ffma2_rn(f2(dp[2 * i], dp[2 * i + 1]), sc, nd);
+    float2 dpe = f2(dp[2 * i], dp[2 * i + 1]);
+    if (DROP) {  // dP = (dO V^T) o mask / (1-p)
+      const uint32_t bits = drop_pair_bits(drop_rk, static_cast<uint32_t>(kv0 + 2 * i) >> 1);
+      dpe.x = drop_keep_lo(bits, dcfg.thr16) ? dpe.x * dcfg.inv_keep : 0.f;
+      dpe.y = drop_keep_hi(bits, dcfg.thr16) ? dpe.y * dcfg.inv_keep : 0.f;
+    }
+    const float2 u = __ffma2_rn(dpe, sc, nd);
     float2 d = __fmul2_rn(p, u);
     if (MODE == kDiag) {  // keep column <= row
       d.x = (2 * i <= lane) ? d.x : 0.f;
@@ -155,9 +162,10 @@ __device__ __forceinline__ void dq_chunk(uint32_t taddr_s, uint32_t taddr_dp, in
 
 // backward (dK/dV kernel): P^T and dS^T for one chunk; statistics are per COLUMN (query), read from shared memory.
 // MODE kDiag here is the general path: keep iff (q >= kv) && (q < T).
-template <int MODE>
+template <int MODE, bool DROP>
 __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, uint32_t st_lse2, uint32_t st_delta8,
-                                          int q_base, int kv_t, int T, uint32_t* pk_p, uint32_t* pk_ds) {
+                                          int q_base, int kv_t, int T, uint32_t* pk_p, uint32_t* pk_ds, const DropCfg& dcfg,
+                                          uint32_t st_rowkey) {
   if (MODE == kMasked) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; pk_ds[i] = 0u; }
@@ -179,15 +187,29 @@ __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, u
       const float2 nd = h == 0 ? make_float2(d4.x, d4.y) : make_float2(d4.z, d4.w);
       const float2 t = __ffma2_rn(f2(s[2 * i], s[2 * i + 1]), sl, nl);
       float2 p = make_float2(ex2(t.x), ex2(t.y));
-      const float2 u = __ffma2_rn(f2(dp[2 * i], dp[2 * i + 1]), sc, nd);
+      float2 dpe = f2(dp[2 * i], dp[2 * i + 1]);
+      float2 pd = p;  // the (dropped) probabilities that multiply dO in dV
+      if (DROP) {
+        // the mask row is the QUERY (a column here), so every element needs its own hash: lane (kv & 1) of pair kv >> 1
+        uint32_t rk0, rk1;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rk0), "=r"(rk1) : "r"(st_rowkey + 8 * i));
+        const uint32_t sh = (kv_t & 1) * 16, pr = static_cast<uint32_t>(kv_t) >> 1;
+        const bool k0 = ((drop_pair_bits(rk0, pr) >> sh) & 0xFFFFu) >= dcfg.thr16;
+        const bool k1 = ((drop_pair_bits(rk1, pr) >> sh) & 0xFFFFu) >= dcfg.thr16;
+        pd.x = k0 ? p.x * dcfg.inv_keep : 0.f;
+        pd.y = k1 ? p.y * dcfg.inv_keep : 0.f;
+        dpe.x = k0 ? dpe.x * dcfg.inv_keep : 0.f;
+        dpe.y = k1 ? dpe.y * dcfg.inv_keep : 0.f;
+      }
+      const float2 u = __ffma2_rn(dpe, sc, nd);
       float2 d = __fmul2_rn(p, u);
       if (MODE == kDiag) {
         const int q0 = q_base + 2 * i;
         const bool k0 = (q0 >= kv_t) && (q0 < T), k1 = (q0 + 1 >= kv_t) && (q0 + 1 < T);
-        p.x = k0 ? p.x : 0.f; d.x = k0 ? d.x : 0.f;
-        p.y = k1 ? p.y : 0.f; d.y = k1 ? d.y : 0.f;
+        pd.x = k0 ? pd.x : 0.f; d.x = k0 ? d.x : 0.f;
+        pd.y = k1 ? pd.y : 0.f; d.y = k1 ? d.y : 0.f;
       }
-      pk_p[i] = ptx::pack_bf16x2(p.x, p.y);
+      pk_p[i] = ptx::pack_bf16x2(pd.x, pd.y);
       pk_ds[i] = ptx::pack_bf16x2(d.x, d.y);
     }
   }
@@ -212,8 +234,11 @@ struct FwdSmem {
 constexpr float kRescaleThreshold = 64.0f;  // log2 units
 
 // p = 2^(s*sl2 - m_ref) for one 32-column chunk, also tracks the raw row max; MODE as for the other chunk helpers
-template <int MODE>
-__device__ __forceinline__ void fwd_chunk(uint32_t taddr, int lane, float neg_m, float& tmax, float& rowsum, uint32_t* pk) {
+// DROP: attention dropout (SDPA dropout_p, model.py:64): the row sum uses the undropped probabilities, the P fed to P V is
+// masked and scaled by 1/(1-p); mask bit = f(site key, row (b,h,q), key position), regenerated in the backward kernels.
+template <int MODE, bool DROP>
+__device__ __forceinline__ void fwd_chunk(uint32_t taddr, int lane, float neg_m, float& tmax, float& rowsum, uint32_t* pk,
+                                          const DropCfg& dcfg, uint32_t drop_rk, int kv0) {
   if (MODE == kMasked) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = 0u;
@@ -239,10 +264,18 @@ __device__ __forceinline__ void fwd_chunk(uint32_t taddr, int lane, float neg_m,
     m1 = fmaxf(m1, fmaxf(s2, s3));
     const float2 t0 = __ffma2_rn(make_float2(s0, s1), sl, nm);
     const float2 t1 = __ffma2_rn(make_float2(s2, s3), sl, nm);
-    const float2 p0 = make_float2(ex2(t0.x), ex2(t0.y));  // masked entries: 2^(-huge) = 0
-    const float2 p1 = make_float2(ex2(t1.x), ex2(t1.y));
+    float2 p0 = make_float2(ex2(t0.x), ex2(t0.y));  // masked entries: 2^(-huge) = 0
+    float2 p1 = make_float2(ex2(t1.x), ex2(t1.y));
     acc0 = __fadd2_rn(acc0, p0);
     acc1 = __fadd2_rn(acc1, p1);
+    if (DROP) {
+      const uint32_t b0 = drop_pair_bits(drop_rk, static_cast<uint32_t>(kv0 + 2 * i) >> 1);
+      const uint32_t b1 = drop_pair_bits(drop_rk, static_cast<uint32_t>(kv0 + 2 * i + 2) >> 1);
+      p0.x = drop_keep_lo(b0, dcfg.thr16) ? p0.x * dcfg.inv_keep : 0.f;
+      p0.y = drop_keep_hi(b0, dcfg.thr16) ? p0.y * dcfg.inv_keep : 0.f;
+      p1.x = drop_keep_lo(b1, dcfg.thr16) ? p1.x * dcfg.inv_keep : 0.f;
+      p1.y = drop_keep_hi(b1, dcfg.thr16) ? p1.y * dcfg.inv_keep : 0.f;
+    }
     pk[i] = ptx::pack_bf16x2(p0.x, p0.y);
     pk[i + 1] = ptx::pack_bf16x2(p1.x, p1.y);
   }
@@ -250,20 +283,24 @@ __device__ __forceinline__ void fwd_chunk(uint32_t taddr, int lane, float neg_m,
   rowsum += (acc0.x + acc0.y) + (acc1.x + acc1.y);
 }
 
+template <bool DROP>
 __device__ __forceinline__ void fwd_tile(uint32_t tm_s, int lane, int cls0, int cls1, float neg_m, float& tmax, float& rowsum,
-                                         uint32_t* pk) {
+                                         uint32_t* pk, const DropCfg& dcfg, uint32_t drop_rk, int kv_tile0) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const int cls = c == 0 ? cls0 : cls1;
-    if (cls == kFull) fwd_chunk<kFull>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16);
-    else if (cls == kDiag) fwd_chunk<kDiag>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16);
-    else fwd_chunk<kMasked>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16);
+    const int kv0 = kv_tile0 + c * 32;
+    if (cls == kFull) fwd_chunk<kFull, DROP>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16, dcfg, drop_rk, kv0);
+    else if (cls == kDiag) fwd_chunk<kDiag, DROP>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16, dcfg, drop_rk, kv0);
+    else fwd_chunk<kMasked, DROP>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16, dcfg, drop_rk, kv0);
   }
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int C, long long* trace) {
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int C, long long* trace,
+                const DropCfg dcfg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR);
@@ -369,6 +406,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t sP = ptx::smem_u32(smem + FwdSmem::P);
     const int r0 = qt * 128 + quarter * 32;  // first query row of this warp (relative to the sequence)
     float m_ref = 0.f, l = 0.f;
+    const uint32_t drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(blockIdx.y * T + qt * 128 + r));
     for (int j = 0; j < num_kv; ++j) {
       const int bsel = j & 1;
       const uint32_t tm_s = tmem_base + lane_off + bsel * 64;
@@ -391,9 +429,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           else if (cls == kDiag) tmax = fmaxf(tmax, fwd_chunk_max<kDiag>(tm_s + c * 32, lane));
         }
         m_ref = tmax * kSl2;
-        fwd_tile(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk);
+        fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
       } else {
-        fwd_tile(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk);
+        fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
         const bool need = tmax * kSl2 - m_ref > kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
           // rare: raise the reference, rescale the O accumulator in TMEM, recompute this tile's P
@@ -415,7 +453,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           m_ref = m_new;
           tmax = -1e30f;
           rowsum = 0.f;
-          fwd_tile(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk);
+          fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
         }
       }
       l += rowsum;
@@ -501,10 +539,12 @@ struct DqSmem {
   static constexpr int TOTAL = BAR + 256 + 1024;
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                    const __grid_constant__ CUtensorMap tmDO128, const float* __restrict__ lse,
-                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, long long* trace) {
+                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, long long* trace,
+                   const DropCfg dcfg) {
   const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
 #define DQ_STAMP(k) do { if (tr) trace[j * 8 + (k)] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
@@ -626,6 +666,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     const float neg_lse2 = valid ? -__ldg(lse + stat_idx) * kLog2e : 0.f;
     const float neg_delta8 = valid ? -__ldg(delta + stat_idx) * kScale : 0.f;
     const int r0 = qt * 128 + quarter * 32;
+    const uint32_t drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(blockIdx.y * T + t));
     for (int j = g; j < num_kv; j += 2) {
       const int use = j >> 1;
       DQ_STAMP(0);
@@ -637,9 +678,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
       for (int c = 0; c < 2; ++c) {
         const int c0 = j * 64 + c * 32;
         const uint32_t ta_s = tmem_base + lane_off + (j % kSBuf) * 128 + c * 32, ta_dp = ta_s + 64;
-        if (c0 + 31 <= r0) dq_chunk<kFull>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
-        else if (c0 > r0 + 31) dq_chunk<kMasked>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
-        else dq_chunk<kDiag>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16);
+        if (c0 + 31 <= r0) dq_chunk<kFull, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16, dcfg, drop_rk, c0);
+        else if (c0 > r0 + 31) dq_chunk<kMasked, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16, dcfg, drop_rk, c0);
+        else dq_chunk<kDiag, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16, dcfg, drop_rk, c0);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_free[j % kSBuf]);  // both score tiles of this step are in registers
@@ -684,15 +725,17 @@ struct DkvSmem {
   static constexpr int QDO = 32768;    // kRing stages x (Q 64x64 | dO 64x64)
   static constexpr int PT = QDO + kRing * 16384;  // 2 buffers x 128 x 64   P^T
   static constexpr int DST = PT + 2 * 16384;      // 2 buffers x 128 x 64   dS^T
-  static constexpr int STAT = DST + 2 * 16384;    // 2 groups x 2 buffers x (-lse2[64] | -delta8[64]) fp32
-  static constexpr int BAR = STAT + 2048;
+  static constexpr int STAT = DST + 2 * 16384;    // 2 groups x 2 buffers x (-lse2[64] | -delta8[64] | dropout row key[64])
+  static constexpr int BAR = STAT + 3072;
   static constexpr int TOTAL = BAR + 256 + 1024;
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                     const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
-                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, long long* trace) {
+                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, long long* trace,
+                    const DropCfg dcfg) {
   const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
 #define DKV_STAMP(k) do { if (tr) trace[128 + n * 8 + (k)] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
@@ -818,12 +861,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     for (int n = g; n < nq; n += 2) {
       const int use = n >> 1;
       const int q0 = (i0 + n) * 64;
-      float* st_lse = stat + (g * 2 + (use & 1)) * 128;
+      float* st_lse = stat + (g * 2 + (use & 1)) * 192;
       {
         const int qi = q0 + (tid & 63);
         float v = 0.f;
         if (qi < T) v = (tid < 64) ? -__ldg(lse + stat_base + qi) * kLog2e : -__ldg(delta + stat_base + qi) * kScale;
         st_lse[tid] = v;
+        if (DROP && tid < 64)
+          st_lse[128 + tid] = __uint_as_float(drop_row_key(dcfg.key, static_cast<uint32_t>(blockIdx.y * T + qi)));
       }
       DKV_STAMP(0);
       ptx::bar_sync(1 + g, 128);
@@ -835,10 +880,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       for (int c = 0; c < 2; ++c) {
         const int c0 = q0 + c * 32;
         const uint32_t ta_s = tmem_base + lane_off + (n % kSBuf) * 128 + c * 32, ta_dp = ta_s + 64;
-        const uint32_t l2 = ptx::smem_u32(st_lse) + c * 128, d8 = l2 + 256;
-        if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
-        else if (c0 + 31 < r0 || c0 >= T) dkv_chunk<kMasked>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
-        else dkv_chunk<kDiag>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16);
+        const uint32_t l2 = ptx::smem_u32(st_lse) + c * 128, d8 = l2 + 256, rkeys = l2 + 512;
+        if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16, dcfg, rkeys);
+        else if (c0 + 31 < r0 || c0 >= T) dkv_chunk<kMasked, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16, dcfg, rkeys);
+        else dkv_chunk<kDiag, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16, dcfg, rkeys);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_free[n % kSBuf]);
@@ -899,32 +944,41 @@ int check_shape(const char* who, int B, int T, int H) {
 
 }  // namespace
 
-int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, cudaStream_t stream) {
+int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float drop_p, uint32_t drop_key,
+             cudaStream_t stream) {
   int rc = check_shape("attn_fwd", B, T, H);
   if (rc) return rc;
   ABCGPT_CHECK_ARG(qkv && out && lse, "attn_fwd: null pointer");
+  ABCGPT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "attn_fwd: dropout p must be in [0, 1)");
   const int C = H * HS;
+  const DropCfg dcfg = make_drop(drop_p, drop_key);
   CUtensorMap tmQ, tmKV;
   if ((rc = encode_tmap_2d(&tmQ, qkv, 2, 3ull * C, static_cast<uint64_t>(B) * T, 3ull * C * 2, 64, 128, true))) return rc;
   if ((rc = encode_tmap_2d(&tmKV, qkv, 2, 3ull * C, static_cast<uint64_t>(B) * T, 3ull * C * 2, 64, 64, true))) return rc;
   static bool done = false;
   if (!done) {
-    rc = set_smem(attn_fwd_kernel, FwdSmem::TOTAL);
-    if (rc) return rc;
+    if ((rc = set_smem(attn_fwd_kernel<false>, FwdSmem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_fwd_kernel<true>, FwdSmem::TOTAL))) return rc;
     done = true;
   }
   dim3 grid((T + 127) / 128, B * H);
-  attn_fwd_kernel<<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse, T, H, C,
-                                                              g_attn_trace);
+  if (dcfg.thr16 == 0)
+    attn_fwd_kernel<false><<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
+                                                                       T, H, C, g_attn_trace, dcfg);
+  else
+    attn_fwd_kernel<true><<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
+                                                                      T, H, C, g_attn_trace, dcfg);
   return launch_status("attn_fwd_kernel");
 }
 
 int attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
-             int T, int H, cudaStream_t stream) {
+             int T, int H, float drop_p, uint32_t drop_key, cudaStream_t stream) {
   int rc = check_shape("attn_bwd", B, T, H);
   if (rc) return rc;
   ABCGPT_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "attn_bwd: null pointer");
+  ABCGPT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "attn_bwd: dropout p must be in [0, 1)");
   const int C = H * HS;
+  const DropCfg dcfg = make_drop(drop_p, drop_key);
   const uint64_t rows = static_cast<uint64_t>(B) * T;
   CUtensorMap tmQKV128, tmQKV64, tmDO128, tmDO64;
   if ((rc = encode_tmap_2d(&tmQKV128, qkv, 2, 3ull * C, rows, 3ull * C * 2, 64, 128, true))) return rc;
@@ -933,8 +987,10 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
   if ((rc = encode_tmap_2d(&tmDO64, dout, 2, static_cast<uint64_t>(C), rows, static_cast<uint64_t>(C) * 2, 64, 64, true))) return rc;
   static bool done = false;
   if (!done) {
-    if ((rc = set_smem(attn_bwd_dq_kernel, DqSmem::TOTAL))) return rc;
-    if ((rc = set_smem(attn_bwd_dkv_kernel, DkvSmem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dq_kernel<false>, DqSmem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dq_kernel<true>, DqSmem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dkv_kernel<false>, DkvSmem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dkv_kernel<true>, DkvSmem::TOTAL))) return rc;
     done = true;
   }
   {
@@ -944,11 +1000,20 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
     if ((rc = launch_status("attn_delta_kernel"))) return rc;
   }
   dim3 grid((T + 127) / 128, B * H);
-  attn_bwd_dkv_kernel<<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta,
-                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, C, g_attn_trace);
-  if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
-  attn_bwd_dq_kernel<<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta,
-                                                               reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, C, g_attn_trace);
+  __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  if (dcfg.thr16 == 0) {
+    attn_bwd_dkv_kernel<false><<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
+                                                                              g_attn_trace, dcfg);
+    if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
+    attn_bwd_dq_kernel<false><<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
+                                                                            g_attn_trace, dcfg);
+  } else {
+    attn_bwd_dkv_kernel<true><<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
+                                                                             g_attn_trace, dcfg);
+    if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
+    attn_bwd_dq_kernel<true><<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
+                                                                           g_attn_trace, dcfg);
+  }
   return launch_status("attn_bwd_dq_kernel");
 }
 

@@ -2,6 +2,7 @@
 // cross-entropy for the small ABC vocabulary, gradient sum-of-squares, fused clip + AdamW (+ bf16 weight
 // shadow), casts and the greedy sampling head.  All global traffic is 128-bit where alignment allows.
 #include "common.h"
+#include "dropout.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -19,10 +20,21 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// scale-or-zero the four columns [4*c4, 4*c4+4) of `row` according to the dropout mask of this site
+__device__ __forceinline__ void drop4(float4& v, const DropCfg& d, uint32_t row, int c4) {
+  if (d.thr16 == 0) return;
+  const uint32_t rk = drop_row_key(d.key, row);
+  const uint32_t b0 = drop_pair_bits(rk, 2 * c4), b1 = drop_pair_bits(rk, 2 * c4 + 1);
+  v.x = drop_keep_lo(b0, d.thr16) ? v.x * d.inv_keep : 0.f;
+  v.y = drop_keep_hi(b0, d.thr16) ? v.y * d.inv_keep : 0.f;
+  v.z = drop_keep_lo(b1, d.thr16) ? v.z * d.inv_keep : 0.f;
+  v.w = drop_keep_hi(b1, d.thr16) ? v.w * d.inv_keep : 0.f;
+}
+
 // ---- embedding (model.py:177-179) ----------------------------------------------------------------------
 __global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float4* __restrict__ wte,
                                  const float4* __restrict__ wpe, float4* __restrict__ x, long long total, int T,
-                                 int C4, int V) {
+                                 int C4, int V, DropCfg drop) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long m = i / C4;
@@ -32,18 +44,22 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float4* 
     const int t = static_cast<int>(m % T);
     const float4 a = __ldg(wte + tok * C4 + c);
     const float4 b = __ldg(wpe + static_cast<long long>(t) * C4 + c);
-    x[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    drop4(o, drop, static_cast<uint32_t>(m), c);
+    x[i] = o;
   }
 }
 
 // dwpe[t,:] += sum_b dx[b,t,:]  (deterministic: one thread per (t, 4 columns), loops over the batch)
-__global__ void embed_bwd_wpe_kernel(const float4* __restrict__ dx, float4* __restrict__ dwpe, int B, int T, int C4) {
+__global__ void embed_bwd_wpe_kernel(const float4* __restrict__ dx, float4* __restrict__ dwpe, int B, int T, int C4,
+                                     DropCfg drop) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(T) * C4) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long stride = static_cast<long long>(T) * C4;
   for (int b = 0; b < B; ++b) {
-    const float4 v = __ldg(dx + b * stride + i);
+    float4 v = __ldg(dx + b * stride + i);
+    drop4(v, drop, static_cast<uint32_t>(b * T + i / C4), static_cast<int>(i % C4));
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   float4 o = dwpe[i];
@@ -58,7 +74,7 @@ __global__ void embed_bwd_wpe_kernel(const float4* __restrict__ dx, float4* __re
 constexpr int kWteCols = 128;
 __global__ void __launch_bounds__(256)
 embed_bwd_wte_smem_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dx, float* __restrict__ dwte,
-                          int M, int C, int V, int rows_per_block) {
+                          int M, int C, int V, int rows_per_block, DropCfg drop) {
   extern __shared__ float table[];  // [V][kWteCols]
   const int col0 = blockIdx.y * kWteCols;
   const int ncols = min(kWteCols, C - col0);
@@ -72,7 +88,8 @@ embed_bwd_wte_smem_kernel(const int64_t* __restrict__ idx, const float* __restri
     if (tok < 0 || tok >= V) continue;
     const int c = lane * 4;
     if (c < ncols) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(dx + static_cast<long long>(m) * C + col0 + c));
+      float4 v = __ldg(reinterpret_cast<const float4*>(dx + static_cast<long long>(m) * C + col0 + c));
+      drop4(v, drop, static_cast<uint32_t>(m), (col0 + c) >> 2);
       float* t = table + tok * kWteCols + c;
       atomicAdd(t + 0, v.x); atomicAdd(t + 1, v.y); atomicAdd(t + 2, v.z); atomicAdd(t + 3, v.w);
     }
@@ -88,14 +105,15 @@ embed_bwd_wte_smem_kernel(const int64_t* __restrict__ idx, const float* __restri
   }
 }
 __global__ void embed_bwd_wte_direct_kernel(const int64_t* __restrict__ idx, const float4* __restrict__ dx,
-                                            float* __restrict__ dwte, long long total, int C4, int V) {
+                                            float* __restrict__ dwte, long long total, int C4, int V, DropCfg drop) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long m = i / C4;
     const int c = static_cast<int>(i - m * C4);
     const long long tok = __ldg(idx + m);
     if (tok < 0 || tok >= V) continue;
-    const float4 v = __ldg(dx + i);
+    float4 v = __ldg(dx + i);
+    drop4(v, drop, static_cast<uint32_t>(m), c);
     ptx::red_add_v4(dwte + (tok * C4 + c) * 4, v.x, v.y, v.z, v.w);
   }
 }
@@ -348,26 +366,28 @@ inline int grid_for(long long work_items, int threads, int waves = 8) {
 
 }  // namespace
 
-int embed_fwd(const int64_t* idx, const float* wte, const float* wpe, float* x, int M, int T, int C, int V,
-              cudaStream_t stream) {
+int embed_fwd(const int64_t* idx, const float* wte, const float* wpe, float* x, int M, int T, int C, int V, float drop_p,
+              uint32_t drop_key, cudaStream_t stream) {
+  const DropCfg drop = make_drop(drop_p, drop_key);
   ABCGPT_CHECK_ARG(idx && wte && wpe && x, "embed_fwd: null pointer");
   ABCGPT_CHECK_ARG(M > 0 && T > 0 && C % 4 == 0 && V > 0, "embed_fwd: bad shape M=%d T=%d C=%d V=%d", M, T, C, V);
   const long long total = static_cast<long long>(M) * (C / 4);
   embed_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(idx, reinterpret_cast<const float4*>(wte),
                                                              reinterpret_cast<const float4*>(wpe),
-                                                             reinterpret_cast<float4*>(x), total, T, C / 4, V);
+                                                             reinterpret_cast<float4*>(x), total, T, C / 4, V, drop);
   return launch_status("embed_fwd_kernel");
 }
 
-int embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int M, int T, int C, int V,
-              cudaStream_t stream) {
+int embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int M, int T, int C, int V, float drop_p,
+              uint32_t drop_key, cudaStream_t stream) {
+  const DropCfg drop = make_drop(drop_p, drop_key);
   ABCGPT_CHECK_ARG(idx && dx && dwte && dwpe, "embed_bwd: null pointer");
   ABCGPT_CHECK_ARG(M > 0 && T > 0 && M % T == 0 && C % 4 == 0 && V > 0, "embed_bwd: bad shape M=%d T=%d C=%d V=%d", M, T, C, V);
   const int C4 = C / 4;
   {
     const long long n = static_cast<long long>(T) * C4;
     embed_bwd_wpe_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, stream>>>(
-        reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dwpe), M / T, T, C4);
+        reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dwpe), M / T, T, C4, drop);
     int rc = launch_status("embed_bwd_wpe_kernel");
     if (rc) return rc;
   }
@@ -380,12 +400,12 @@ int embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int
     }
     const int rows_per_block = 512;
     dim3 grid((M + rows_per_block - 1) / rows_per_block, (C + kWteCols - 1) / kWteCols);
-    embed_bwd_wte_smem_kernel<<<grid, 256, table_bytes, stream>>>(idx, dx, dwte, M, C, V, rows_per_block);
+    embed_bwd_wte_smem_kernel<<<grid, 256, table_bytes, stream>>>(idx, dx, dwte, M, C, V, rows_per_block, drop);
     return launch_status("embed_bwd_wte_smem_kernel");
   }
   const long long total = static_cast<long long>(M) * C4;
   embed_bwd_wte_direct_kernel<<<grid_for(total, 256), 256, 0, stream>>>(idx, reinterpret_cast<const float4*>(dx), dwte,
-                                                                        total, C4, V);
+                                                                        total, C4, V, drop);
   return launch_status("embed_bwd_wte_direct_kernel");
 }
 

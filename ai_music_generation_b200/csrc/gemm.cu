@@ -13,6 +13,7 @@
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 #include "common.h"
+#include "dropout.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -39,6 +40,7 @@ struct GemmParams {
   long long ldaux;
   const float* bias;
   int wide;  // 1: every epilogue pointer / leading dimension is 32-byte aligned -> 256-bit global accesses
+  DropCfg drop;  // RESID epilogue only: dropout on the Linear output before the residual add (model.py:75-76,91)
   unsigned long long* stats;  // optional debug counters (cycles): [0] producer empty-wait, [1] mma full-wait,
                               // [2] mma tmem-empty wait, [3] epilogue tmem-full wait, [4] epilogue busy, [5] cta total
 };
@@ -184,6 +186,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
   } else if constexpr (EPI == ABCGPT_EPI_RESID) {
     // x_out(fp32) = x_in(fp32) + bf16(acc): the reference adds the bf16 Linear output into the fp32 stream
     float* xout = reinterpret_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
+    const uint32_t drop_rk = drop_row_key(p.drop.key, static_cast<uint32_t>(row));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {  // 8 columns per 32-byte group
       if (8 * j < ncols) {
@@ -191,8 +194,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t b = ptx::pack_bf16x2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
-          o[2 * q] = __float_as_uint(__uint_as_float(aux.v[j].v[2 * q]) + ptx::bf16lo(b));
-          o[2 * q + 1] = __float_as_uint(__uint_as_float(aux.v[j].v[2 * q + 1]) + ptx::bf16hi(b));
+          float y0 = ptx::bf16lo(b), y1 = ptx::bf16hi(b);
+          if (p.drop.thr16 != 0) {  // bf16 dropout like nn.Dropout on the bf16 Linear output: scale, round, or zero
+            const uint32_t bits = drop_pair_bits(drop_rk, static_cast<uint32_t>(col0 + 8 * j + 2 * q) >> 1);
+            y0 = drop_keep_lo(bits, p.drop.thr16) ? ptx::bf16_round(y0 * p.drop.inv_keep) : 0.f;
+            y1 = drop_keep_hi(bits, p.drop.thr16) ? ptx::bf16_round(y1 * p.drop.inv_keep) : 0.f;
+          }
+          o[2 * q] = __float_as_uint(__uint_as_float(aux.v[j].v[2 * q]) + y0);
+          o[2 * q + 1] = __float_as_uint(__uint_as_float(aux.v[j].v[2 * q + 1]) + y1);
         }
         if (p.wide) {
           ptx::stg256(xout + 8 * j, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
@@ -651,11 +660,13 @@ int dispatch_major2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const C
 
 int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, long long ldb, int M, int N, int K,
               int epi, void* c, long long ldc, void* c2, long long ldc2, const void* aux, long long ldaux,
-              const float* bias, int bn_hint, int splits_hint, cudaStream_t stream) {
+              const float* bias, int bn_hint, int splits_hint, float drop_p, uint32_t drop_key, cudaStream_t stream) {
 
   ABCGPT_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M,N,K must be positive (got %d,%d,%d)", M, N, K);
   ABCGPT_CHECK_ARG(N % 8 == 0, "gemm: N must be a multiple of 8 (pad the output; got %d)", N);
   ABCGPT_CHECK_ARG(c != nullptr, "gemm: null output");
+  ABCGPT_CHECK_ARG(drop_p == 0.f || (epi == ABCGPT_EPI_RESID && drop_p > 0.f && drop_p < 1.f),
+                   "gemm: dropout is fused into the RESID epilogue only (0 <= p < 1)");
   ABCGPT_CHECK_ARG(epi != ABCGPT_EPI_GELU || c2 != nullptr, "gemm: GELU epilogue needs the second output");
   ABCGPT_CHECK_ARG((epi != ABCGPT_EPI_RESID && epi != ABCGPT_EPI_DGELU) || aux != nullptr,
                    "gemm: epilogue %d needs the aux input", epi);
@@ -722,7 +733,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   p.M = M; p.N = N; p.K = K;
   p.num_m_blk = num_m_blk; p.num_n_blk = num_n_blk; p.num_k_blk = num_k_blk;
   p.splits = splits; p.kb_per_split = kb_per_split;
-  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.stats = g_gemm_stats;
+  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.stats = g_gemm_stats; p.drop = make_drop(drop_p, drop_key);
   {
     const bool f32_out = (epi == ABCGPT_EPI_RESID || epi == ABCGPT_EPI_F32 || epi == ABCGPT_EPI_F32_RED);
     const long long cb = f32_out ? 4 : 2, ab = (epi == ABCGPT_EPI_RESID) ? 4 : 2;

@@ -9,22 +9,23 @@ namespace abcgpt {
 
 int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, long long ldb, int M, int N, int K,
               int epi, void* c, long long ldc, void* c2, long long ldc2, const void* aux, long long ldaux,
-              const float* bias, int bn_hint, int splits_hint, cudaStream_t stream);
+              const float* bias, int bn_hint, int splits_hint, float drop_p, uint32_t drop_key, cudaStream_t stream);
 
-int embed_fwd(const int64_t* idx, const float* wte, const float* wpe, float* x, int M, int T, int C, int V,
-              cudaStream_t stream);
-int embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int M, int T, int C, int V,
-              cudaStream_t stream);
+int embed_fwd(const int64_t* idx, const float* wte, const float* wpe, float* x, int M, int T, int C, int V, float drop_p,
+              uint32_t drop_key, cudaStream_t stream);
+int embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int M, int T, int C, int V, float drop_p,
+              uint32_t drop_key, cudaStream_t stream);
 
 int layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* y_f32, float* mean,
                   float* rstd, int M, int C, cudaStream_t stream);
 int layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean, const float* rstd,
                   const float* dresid_in, float* dx_out, void* dx_bf16, float* dweight, float* dbias, int M, int C,
-                  cudaStream_t stream);
+                  float drop_p, uint32_t drop_key, cudaStream_t stream);
 
-int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, cudaStream_t stream);
+int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float drop_p, uint32_t drop_key,
+             cudaStream_t stream);
 int attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
-             int T, int H, cudaStream_t stream);
+             int T, int H, float drop_p, uint32_t drop_key, cudaStream_t stream);
 
 int ce_fwd(const void* logits, long long ldl, const int64_t* targets, float* row_loss, int M, int V,
            cudaStream_t stream);

@@ -5,6 +5,7 @@
 // consumes (the reference rounds the fp32 LN output to bf16 at the autocast boundary of nn.Linear), the
 // backward fuses the residual-gradient add and emits both the fp32 stream gradient and its bf16 copy.
 #include "common.h"
+#include "dropout.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
               float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ dw, float* __restrict__ db,
-              int M, int C) {
+              int M, int C, DropCfg drop) {
   extern __shared__ float red[];  // [kWarpsPerBlock][C] reused for dweight then dbias
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -146,7 +147,20 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         dxr[idx] = o;
-        if (dxbr) dxbr[idx] = make_uint2(ptx::pack_bf16x2(o.x, o.y), ptx::pack_bf16x2(o.z, o.w));
+        if (dxbr) {
+          // the bf16 copy feeds the backward of the Linear whose OUTPUT was dropped out in the forward: it carries that
+          // site's mask (the fp32 stream gradient above does not: the skip connection is not dropped)
+          uint32_t lo = ptx::pack_bf16x2(o.x, o.y), hi = ptx::pack_bf16x2(o.z, o.w);
+          if (drop.thr16 != 0) {
+            const uint32_t rk = drop_row_key(drop.key, static_cast<uint32_t>(row));
+            const uint32_t b0 = drop_pair_bits(rk, 2 * idx), b1 = drop_pair_bits(rk, 2 * idx + 1);
+            lo = ptx::pack_bf16x2(drop_keep_lo(b0, drop.thr16) ? ptx::bf16lo(lo) * drop.inv_keep : 0.f,
+                                  drop_keep_hi(b0, drop.thr16) ? ptx::bf16hi(lo) * drop.inv_keep : 0.f);
+            hi = ptx::pack_bf16x2(drop_keep_lo(b1, drop.thr16) ? ptx::bf16lo(hi) * drop.inv_keep : 0.f,
+                                  drop_keep_hi(b1, drop.thr16) ? ptx::bf16hi(hi) * drop.inv_keep : 0.f);
+          }
+          dxbr[idx] = make_uint2(lo, hi);
+        }
       }
     }
   }
@@ -200,7 +214,8 @@ int layernorm_fwd(const float* x, const float* weight, const float* bias, void* 
 
 int layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean, const float* rstd,
                   const float* dresid_in, float* dx_out, void* dx_bf16, float* dweight, float* dbias, int M, int C,
-                  cudaStream_t stream) {
+                  float drop_p, uint32_t drop_key, cudaStream_t stream) {
+  const DropCfg drop = make_drop(drop_p, drop_key);
   ABCGPT_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0 && C <= 2048, "layernorm: need C %% 4 == 0 and C <= 2048 (got %d)", C);
   ABCGPT_CHECK_ARG(dy_bf16 && x && weight && mean && rstd && dx_out, "layernorm_bwd: null pointer");
   const int nv = (C + 127) / 128;
@@ -214,7 +229,7 @@ int layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, cons
       if (smem > 48 * 1024) ABCGPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       kern<<<grid, kWarpsPerBlock * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, weight, mean,
                                                         rstd, dresid_in, dx_out,
-                                                        reinterpret_cast<__nv_bfloat16*>(dx_bf16), dweight, dbias, M, C);
+                                                        reinterpret_cast<__nv_bfloat16*>(dx_bf16), dweight, dbias, M, C, drop);
       return 0;
     };
     int rc = has_bias ? launch(ln_bwd_kernel<NV, true>) : launch(ln_bwd_kernel<NV, false>);

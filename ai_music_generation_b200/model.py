@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _C, ops
+from .dropout import site_key
 from .optim import FusedAdamW
 
 
@@ -127,7 +128,7 @@ class _GPTStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, model, idx, targets):
         bufs = model._forward_plan(idx, targets, keep_activations=True)
-        ctx.model, ctx.bufs, ctx.idx, ctx.targets = model, bufs, idx, targets
+        ctx.model, ctx.bufs, ctx.idx, ctx.targets, ctx.drop = model, bufs, idx, targets, bufs.drop
         B, T = idx.shape
         logits = bufs.logits.view(B, T, -1)[:, :, : model.config.vocab_size]
         ctx.mark_non_differentiable(logits)
@@ -135,7 +136,7 @@ class _GPTStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, _grad_logits, grad_loss):
-        ctx.model._backward_plan(ctx.bufs, ctx.idx, ctx.targets, grad_loss)
+        ctx.model._backward_plan(ctx.bufs, ctx.idx, ctx.targets, grad_loss, ctx.drop)
         return None, None, None, None
 
 
@@ -162,6 +163,8 @@ class GPT(nn.Module):
         self._bufs = {}
         self._shadow_fresh = False
         self._pending_clip = None
+        self._next_dropout_seed = None  # tests / reproducibility: force the seed of the next training forward
+        self.last_dropout_seed = None
         self.require_backward_grad_sync = True
         self._grad_sync = None  # set by ddp.DDP
         self._flatten()
@@ -262,9 +265,16 @@ class GPT(nn.Module):
 
     def _forward_plan(self, idx, targets, keep_activations):
         cfg = self.config
-        if self.training and cfg.dropout != 0.0:
-            raise NotImplementedError("dropout > 0 is not implemented in the sm_100a kernels yet (parity and "
-                                      "benchmark runs use dropout=0.0 like the reference's bench.py)")
+        # Dropout (model.py:39-40,85,129 + SDPA dropout_p :64): counter-based masks, one key per site, derived from a seed
+        # drawn from torch's CPU generator for every forward (reproducible under torch.manual_seed); the backward plan
+        # regenerates the masks from the same keys.  site 0 = embedding, block l: 1+3l probs, 2+3l attn resid, 3+3l MLP.
+        p_drop = float(cfg.dropout) if self.training else 0.0
+        if p_drop > 0.0:
+            seed = self._next_dropout_seed if self._next_dropout_seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+            self._next_dropout_seed = None
+            keys = [site_key(seed, i) for i in range(1 + 3 * cfg.n_layer)]
+        else:
+            seed, keys = None, [0] * (1 + 3 * cfg.n_layer)
         if not idx.is_cuda:
             raise _C.AbcgptError("GPT.forward: idx must be a CUDA tensor (there is no CPU path)")
         self._ensure_device_state()
@@ -275,7 +285,9 @@ class GPT(nn.Module):
         bufs = self._act_buffers(B, T, keep_activations)
         C, H, V = cfg.n_embd, cfg.n_head, cfg.vocab_size
         idx = idx.contiguous()
-        ops.embed_fwd(idx, top["wte"][0], top["wpe"][0], bufs.x[0], T)
+        bufs.drop = (p_drop, keys, seed)
+        self.last_dropout_seed = seed
+        ops.embed_fwd(idx, top["wte"][0], top["wpe"][0], bufs.x[0], T, drop_p=p_drop, drop_key=keys[0])
         for li, lw in enumerate(layers):
             k = li if keep_activations else 0
             x_in, x_out = bufs.x[k], bufs.x[k + 1] if keep_activations else bufs.x[0]
@@ -283,14 +295,14 @@ class GPT(nn.Module):
             b = lambda name: None if lw[name] is None else lw[name][0]  # noqa: E731
             ops.layernorm_fwd(x_in, lw["ln_1.weight"][0], b("ln_1.bias"), bufs.ln1[k], st[0], st[1])
             ops.gemm(bufs.ln1[k], lw["attn.c_attn.weight"][1], epilogue=ops.EPI_BF16, out=bufs.qkv[k], bias=b("attn.c_attn.bias"))
-            ops.attn_fwd(bufs.qkv[k], bufs.att[k], bufs.lse[k], B, T, H)
+            ops.attn_fwd(bufs.qkv[k], bufs.att[k], bufs.lse[k], B, T, H, drop_p=p_drop, drop_key=keys[1 + 3 * li])
             ops.gemm(bufs.att[k], lw["attn.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=bufs.xmid[k], aux=x_in,
-                     bias=b("attn.c_proj.bias"))
+                     bias=b("attn.c_proj.bias"), drop_p=p_drop, drop_key=keys[2 + 3 * li])
             ops.layernorm_fwd(bufs.xmid[k], lw["ln_2.weight"][0], b("ln_2.bias"), bufs.ln2[k], st[2], st[3])
             ops.gemm(bufs.ln2[k], lw["mlp.c_fc.weight"][1], epilogue=ops.EPI_GELU, out=bufs.h[k], out2=bufs.g[k],
                      bias=b("mlp.c_fc.bias"))
             ops.gemm(bufs.g[k], lw["mlp.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=x_out, aux=bufs.xmid[k],
-                     bias=b("mlp.c_proj.bias"))
+                     bias=b("mlp.c_proj.bias"), drop_p=p_drop, drop_key=keys[3 + 3 * li])
         x_last = bufs.x[cfg.n_layer] if keep_activations else bufs.x[0]
         lnf_b = None if top["ln_f.bias"] is None else top["ln_f.bias"][0]
         ops.layernorm_fwd(x_last, top["ln_f.weight"][0], lnf_b, bufs.lnf, bufs.statf[0], bufs.statf[1])
@@ -303,8 +315,9 @@ class GPT(nn.Module):
             ops.gemm(a, wte_bf16, M=B, N=bufs.Vpad, K=C, epilogue=ops.EPI_BF16, out=bufs.last_logits)
         return bufs
 
-    def _backward_plan(self, bufs, idx, targets, grad_loss):
+    def _backward_plan(self, bufs, idx, targets, grad_loss, drop):
         cfg = self.config
+        p_drop, keys, _ = drop
         a = self._arena
         layers = self._layer_tensors()
         top = a["top"]
@@ -324,8 +337,10 @@ class GPT(nn.Module):
         ops.gemm(bufs.dlogits, wte_bf16, b_mn=True, M=M, N=C, K=V, epilogue=ops.EPI_BF16, out=bufs.dln)
         dx, dx_other = bufs.dx[0], bufs.dx[1]
         gw = lambda t: None if t is None else t[2]  # noqa: E731
+        # every bf16 stream gradient `dxb` is produced already masked for the residual-branch dropout of its consumer
         ops.layernorm_bwd(bufs.dln, bufs.x[cfg.n_layer], top["ln_f.weight"][0], bufs.statf[0], bufs.statf[1], None, dx,
-                          bufs.dxb, top["ln_f.weight"][2], gw(top["ln_f.bias"]))
+                          bufs.dxb, top["ln_f.weight"][2], gw(top["ln_f.bias"]), drop_p=p_drop,
+                          drop_key=keys[3 + 3 * (cfg.n_layer - 1)])
         for li in range(cfg.n_layer - 1, -1, -1):
             lw = layers[li]
             st = bufs.stat[li]
@@ -339,24 +354,26 @@ class GPT(nn.Module):
                 ops.colsum_bf16(bufs.dh, lw["mlp.c_fc.bias"][2])
             ops.gemm(bufs.dh, lw["mlp.c_fc.weight"][1], b_mn=True, epilogue=ops.EPI_BF16, out=bufs.dln)
             ops.layernorm_bwd(bufs.dln, bufs.xmid[li], lw["ln_2.weight"][0], st[2], st[3], dx, dx_other, bufs.dxb,
-                              lw["ln_2.weight"][2], gw(lw["ln_2.bias"]))
+                              lw["ln_2.weight"][2], gw(lw["ln_2.bias"]), drop_p=p_drop, drop_key=keys[2 + 3 * li])
             dx, dx_other = dx_other, dx
             # ---- attention: xmid = x_in + c_proj(attn(c_attn(ln_1(x_in))))
             ops.gemm(bufs.dxb, bufs.att[li], a_mn=True, b_mn=True, epilogue=ops.EPI_F32_RED, out=lw["attn.c_proj.weight"][2])
             if lw["attn.c_proj.bias"] is not None:
                 ops.colsum_bf16(bufs.dxb, lw["attn.c_proj.bias"][2])
             ops.gemm(bufs.dxb, lw["attn.c_proj.weight"][1], b_mn=True, epilogue=ops.EPI_BF16, out=bufs.datt)
-            ops.attn_bwd(bufs.qkv[li], bufs.att[li], bufs.datt, bufs.lse[li], bufs.delta, bufs.dqkv, B, T, H)
+            ops.attn_bwd(bufs.qkv[li], bufs.att[li], bufs.datt, bufs.lse[li], bufs.delta, bufs.dqkv, B, T, H,
+                         drop_p=p_drop, drop_key=keys[1 + 3 * li])
             ops.gemm(bufs.dqkv, bufs.ln1[li], a_mn=True, b_mn=True, epilogue=ops.EPI_F32_RED, out=lw["attn.c_attn.weight"][2])
             if lw["attn.c_attn.bias"] is not None:
                 ops.colsum_bf16(bufs.dqkv, lw["attn.c_attn.bias"][2])
             ops.gemm(bufs.dqkv, lw["attn.c_attn.weight"][1], b_mn=True, epilogue=ops.EPI_BF16, out=bufs.dln)
             ops.layernorm_bwd(bufs.dln, bufs.x[li], lw["ln_1.weight"][0], st[0], st[1], dx, dx_other, bufs.dxb,
-                              lw["ln_1.weight"][2], gw(lw["ln_1.bias"]))
+                              lw["ln_1.weight"][2], gw(lw["ln_1.bias"]), drop_p=p_drop if li > 0 else 0.0,
+                              drop_key=keys[3 + 3 * (li - 1)] if li > 0 else 0)
             dx, dx_other = dx_other, dx
             if self._grad_sync is not None and self.require_backward_grad_sync:
                 self._grad_sync.layer_done(li)
-        ops.embed_bwd(idx.contiguous().view(-1), dx, dwte, top["wpe"][2], T)
+        ops.embed_bwd(idx.contiguous().view(-1), dx, dwte, top["wpe"][2], T, drop_p=p_drop, drop_key=keys[0])
         if self._grad_sync is not None and self.require_backward_grad_sync:
             self._grad_sync.backward_done()
 

@@ -58,7 +58,7 @@ def _rowmajor_ld(t, name):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_BF16, out=None, out2=None, aux=None,
-         bias=None, tile_n=0, splits=0):
+         bias=None, tile_n=0, splits=0, drop_p=0.0, drop_key=0):
     """out[M,N] = sum_k A[m,k] B[n,k] (bf16 in, fp32 accumulate on tcgen05).
 
     a: [M,K] (a_mn=False) or stored [K,M] (a_mn=True); b: [N,K] or stored [K,N]."""
@@ -79,24 +79,24 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_B
         _chk(bias, torch.float32, "gemm bias")
     _call("gemm", 1, (M, N, K, int(a_mn), int(b_mn), epilogue), _C.lib().abcgpt_gemm_bf16, a.data_ptr(), int(a_mn), lda,
           b.data_ptr(), int(b_mn), ldb, M, N, K, epilogue, out.data_ptr(), ldc, _ptr(out2), ldc2, _ptr(aux), ldaux,
-          _ptr(bias), tile_n, splits, _stream())
+          _ptr(bias), tile_n, splits, drop_p, drop_key, _stream())
     return out
 
 
-def embed_fwd(idx, wte, wpe, x, T):
+def embed_fwd(idx, wte, wpe, x, T, drop_p=0.0, drop_key=0):
     _chk(idx, torch.int64, "embed idx")
     M = idx.numel()
     V, C = wte.shape
     _call("embed_fwd", 1, (M, C), _C.lib().abcgpt_embed_fwd, idx.data_ptr(), wte.data_ptr(), wpe.data_ptr(), x.data_ptr(),
-          M, T, C, V, _stream())
+          M, T, C, V, drop_p, drop_key, _stream())
     return x
 
 
-def embed_bwd(idx, dx, dwte, dwpe, T):
+def embed_bwd(idx, dx, dwte, dwpe, T, drop_p=0.0, drop_key=0):
     M = idx.numel()
     V, C = dwte.shape
     _call("embed_bwd", 2, (M, C), _C.lib().abcgpt_embed_bwd, idx.data_ptr(), dx.data_ptr(), dwte.data_ptr(),
-          dwpe.data_ptr(), M, T, C, V, _stream())
+          dwpe.data_ptr(), M, T, C, V, drop_p, drop_key, _stream())
 
 
 def layernorm_fwd(x, weight, bias, y_bf16, mean, rstd, y_f32=None):
@@ -106,22 +106,22 @@ def layernorm_fwd(x, weight, bias, y_bf16, mean, rstd, y_f32=None):
           _ptr(y_bf16), _ptr(y_f32), _ptr(mean), _ptr(rstd), M, C, _stream())
 
 
-def layernorm_bwd(dy_bf16, x, weight, mean, rstd, dresid_in, dx_out, dx_bf16, dweight, dbias):
+def layernorm_bwd(dy_bf16, x, weight, mean, rstd, dresid_in, dx_out, dx_bf16, dweight, dbias, drop_p=0.0, drop_key=0):
     M, C = x.shape
     _call("layernorm_bwd", 1, (M, C), _C.lib().abcgpt_layernorm_bwd, dy_bf16.data_ptr(), x.data_ptr(), weight.data_ptr(),
           mean.data_ptr(), rstd.data_ptr(), _ptr(dresid_in), dx_out.data_ptr(), _ptr(dx_bf16), _ptr(dweight),
-          _ptr(dbias), M, C, _stream())
+          _ptr(dbias), M, C, drop_p, drop_key, _stream())
 
 
-def attn_fwd(qkv, out, lse, B, T, H):
+def attn_fwd(qkv, out, lse, B, T, H, drop_p=0.0, drop_key=0):
     _chk(qkv, torch.bfloat16, "attn qkv")
     _call("attn_fwd", 1, (B, T, H), _C.lib().abcgpt_attn_fwd, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, H,
-          _stream())
+          drop_p, drop_key, _stream())
 
 
-def attn_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H):
+def attn_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, drop_p=0.0, drop_key=0):
     _call("attn_bwd", 3, (B, T, H), _C.lib().abcgpt_attn_bwd, qkv.data_ptr(), out.data_ptr(), dout.data_ptr(),
-          lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, T, H, _stream())
+          lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, T, H, drop_p, drop_key, _stream())
 
 
 def ce_fwd(logits, targets, row_loss, sum_count, loss, V):

@@ -137,7 +137,15 @@ def _layer_norm(x, w, b):
     return F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
 
 
-def _attention(qkv, n_head, bf16):
+def _drop(x, mask, p, bf16):
+    """nn.Dropout with an explicit keep-mask: x * mask / (1 - p), rounded to bf16 when the activation is bf16."""
+    if mask is None:
+        return x
+    y = x * mask.to(x.dtype) / (1.0 - p)
+    return _bf(y) if bf16 else y
+
+
+def _attention(qkv, n_head, bf16, drop_mask=None, p=0.0):
     B, T, C3 = qkv.shape
     C = C3 // 3
     hs = C // n_head
@@ -145,13 +153,15 @@ def _attention(qkv, n_head, bf16):
     q = q.view(B, T, n_head, hs).transpose(1, 2)
     k = k.view(B, T, n_head, hs).transpose(1, 2)
     v = v.view(B, T, n_head, hs).transpose(1, 2)
-    if not bf16:  # same call the reference makes (model.py:64); the explicit form below is its definition (:67-71)
+    if not bf16 and drop_mask is None:  # same call the reference makes (model.py:64); the explicit form below is its definition (:67-71)
         y = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=True)
         return y.transpose(1, 2).contiguous().view(B, T, C)
     att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(hs))
     mask = torch.ones(T, T, dtype=torch.bool).tril()
     att = att.masked_fill(~mask, float("-inf"))
     att = torch.softmax(att, dim=-1)
+    if drop_mask is not None:  # attn_dropout (:70) / SDPA dropout_p (:64) on the probabilities
+        att = att * drop_mask.to(att.dtype) / (1.0 - p)
     if bf16:
         att = _bf(att)  # flash kernels feed P to the second matmul in bf16
     y = att @ v
@@ -159,24 +169,30 @@ def _attention(qkv, n_head, bf16):
     return _bf(y) if bf16 else y
 
 
-def forward(sd, cfg: OracleConfig, idx, targets=None, bf16: bool = False, return_hidden: bool = False):
-    """(logits, loss) exactly as GPT.forward: full logits with targets, last position only without."""
+def forward(sd, cfg: OracleConfig, idx, targets=None, bf16: bool = False, return_hidden: bool = False, masks=None):
+    """(logits, loss) exactly as GPT.forward: full logits with targets, last position only without.
+
+    masks (training with dropout): {'p': float, 'emb': bool [B,T,C], 'attn_p': [L x bool [B,H,T,T]],
+    'attn_resid': [L x bool [B,T,C]], 'mlp_resid': [L x bool [B,T,C]]} — the keep-masks nn.Dropout would have drawn."""
     B, T = idx.shape
     assert T <= cfg.block_size
     g = (lambda n: sd.get(n))
     x = sd["transformer.wte.weight"][idx] + sd["transformer.wpe.weight"][:T]
+    pd = masks["p"] if masks else 0.0
+    mk = (lambda name, i=None: None if not masks else (masks[name] if i is None else masks[name][i]))
+    x = _drop(x, mk("emb"), pd, False)
     for i in range(cfg.n_layer):
         p = f"transformer.h.{i}."
         h = _layer_norm(x, sd[p + "ln_1.weight"], g(p + "ln_1.bias"))
         qkv = _linear(h, sd[p + "attn.c_attn.weight"], g(p + "attn.c_attn.bias"), bf16)
-        a = _attention(qkv, cfg.n_head, bf16)
-        x = x + _linear(a, sd[p + "attn.c_proj.weight"], g(p + "attn.c_proj.bias"), bf16)
+        a = _attention(qkv, cfg.n_head, bf16, mk("attn_p", i), pd)
+        x = x + _drop(_linear(a, sd[p + "attn.c_proj.weight"], g(p + "attn.c_proj.bias"), bf16), mk("attn_resid", i), pd, bf16)
         h = _layer_norm(x, sd[p + "ln_2.weight"], g(p + "ln_2.bias"))
         h = _linear(h, sd[p + "mlp.c_fc.weight"], g(p + "mlp.c_fc.bias"), bf16)
         h = F.gelu(h)
         if bf16:
             h = _bf(h)
-        x = x + _linear(h, sd[p + "mlp.c_proj.weight"], g(p + "mlp.c_proj.bias"), bf16)
+        x = x + _drop(_linear(h, sd[p + "mlp.c_proj.weight"], g(p + "mlp.c_proj.bias"), bf16), mk("mlp_resid", i), pd, bf16)
     x = _layer_norm(x, sd["transformer.ln_f.weight"], g("transformer.ln_f.bias"))
     if targets is not None:
         logits = _linear(x, sd["transformer.wte.weight"], None, bf16)
@@ -189,10 +205,10 @@ def forward(sd, cfg: OracleConfig, idx, targets=None, bf16: bool = False, return
     return logits, loss
 
 
-def loss_and_grads(sd, cfg: OracleConfig, idx, targets, bf16: bool = False, loss_scale: float = 1.0):
+def loss_and_grads(sd, cfg: OracleConfig, idx, targets, bf16: bool = False, loss_scale: float = 1.0, masks=None):
     """loss, logits, {name: grad} via autograd over the functional forward (fp32 master weights)."""
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
-    logits, loss = forward(leaf, cfg, idx, targets, bf16=bf16)
+    logits, loss = forward(leaf, cfg, idx, targets, bf16=bf16, masks=masks)
     (loss * loss_scale).backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
     return loss.detach(), logits.detach(), grads
