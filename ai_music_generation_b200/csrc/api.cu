@@ -74,6 +74,9 @@ int abcgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16
 int abcgpt_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream) {
   return cast_f32_to_bf16(x, y_bf16, n, S(stream));
 }
+int abcgpt_attn_decode(const void* cache, void* out, int B, int Tmax, int n_keys, int H, void* stream) {
+  return attn_decode(cache, out, B, Tmax, n_keys, H, S(stream));
+}
 int abcgpt_colsum_bf16(const void* dy, int64_t ld, int M, int N, float* out, void* stream) {
   return colsum_bf16(dy, ld, M, N, out, S(stream));
 }

@@ -333,6 +333,62 @@ colsum_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, int M, int N, 
   }
 }
 
+
+// ---- single-token decode attention over a KV cache (generate(), model.py:305-330, with the O(T^2)-per-token context
+// recompute of the reference replaced by a cache) --------------------------------------------------------------------
+// cache: bf16 [B, Tmax, 3C] holding the c_attn output (q | k | v) of every position decoded so far; the query is the
+// row at position n_keys-1.  One block per (batch, head); HBM-bound (K and V of the sequence are read once).
+__global__ void __launch_bounds__(128)
+attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __restrict__ out, int Tmax, int n_keys, int H,
+                   int C) {
+  extern __shared__ float prob[];  // [n_keys]
+  __shared__ float q[64];
+  __shared__ float red[4];
+  __shared__ float part[2][64];
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* base = cache + static_cast<long long>(b) * Tmax * 3 * C;
+  if (tid < 64) q[tid] = __bfloat162float(base[static_cast<long long>(n_keys - 1) * 3 * C + h * 64 + tid]) * 0.125f;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int k = tid; k < n_keys; k += 128) {
+    const uint4* kr = reinterpret_cast<const uint4*>(base + static_cast<long long>(k) * 3 * C + C + h * 64);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 v = __ldg(kr + j);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s += q[8 * j + 2 * e] * ptx::bf16lo(w[e]) + q[8 * j + 2 * e + 1] * ptx::bf16hi(w[e]);
+    }
+    prob[k] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int k = tid; k < n_keys; k += 128) {
+    const float e = __expf(prob[k] - mx);
+    prob[k] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.0f / ((red[0] + red[1]) + (red[2] + red[3]));
+  // out[d] = sum_k p_k V[k][d]: the flash kernels round P to bf16 before the second matmul; mirror that
+  const int d = tid & 63, half = tid >> 6;
+  float acc = 0.f;
+  for (int k = half; k < n_keys; k += 2)
+    acc += ptx::bf16_round(prob[k] * inv) * __bfloat162float(base[static_cast<long long>(k) * 3 * C + 2 * C + h * 64 + d]);
+  part[half][d] = acc;
+  __syncthreads();
+  if (tid < 64) out[static_cast<long long>(b) * C + h * 64 + tid] = __float2bfloat16_rn(part[0][tid] + part[1][tid]);
+}
+
 // ---- greedy head (model.py:316-328 with top_k=1) -----------------------------------------------------------
 __global__ void __launch_bounds__(256)
 argmax_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl, int V, int64_t* __restrict__ out,
@@ -466,6 +522,22 @@ int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream) 
                    "cast: pointers must be 16/8-byte aligned");
   cast_kernel<<<grid_for(n / 4 + 1, 512, 4), 512, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
   return launch_status("cast_kernel");
+}
+
+int attn_decode(const void* cache, void* out, int B, int Tmax, int n_keys, int H, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(cache && out && B > 0 && H > 0 && n_keys > 0 && n_keys <= Tmax, "attn_decode: bad arguments");
+  ABCGPT_CHECK_ARG(static_cast<size_t>(n_keys) * 4 <= 200 * 1024, "attn_decode: context too long for the probability buffer");
+  const size_t smem = static_cast<size_t>(n_keys) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool done = false;
+    if (!done) {
+      ABCGPT_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      done = true;
+    }
+  }
+  attn_decode_kernel<<<B * H, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(cache),
+                                                   reinterpret_cast<__nv_bfloat16*>(out), Tmax, n_keys, H, H * 64);
+  return launch_status("attn_decode_kernel");
 }
 
 int colsum_bf16(const void* dy, long long ld, int M, int N, float* out, cudaStream_t stream) {

@@ -39,6 +39,7 @@ int adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, long 
           float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,
           cudaStream_t stream);
 int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream);
+int attn_decode(const void* cache, void* out, int B, int Tmax, int n_keys, int H, cudaStream_t stream);
 int colsum_bf16(const void* dy, long long ld, int M, int N, float* out, cudaStream_t stream);
 int argmax_rows(const void* logits, long long ldl, int V, int64_t* out, long long out_stride, int B,
                 cudaStream_t stream);

@@ -122,6 +122,26 @@ class _Buffers:
             self.dlogits = e(M, self.Vpad)
 
 
+class _DecodeState:
+    """Buffers of the single-token decode path: the per-layer cache of c_attn outputs [B, Tmax, 3C] and the [B, *] row
+    buffers of one step."""
+
+    def __init__(self, cfg: GPTConfig, B: int, Tmax: int, device):
+        C, L = cfg.n_embd, cfg.n_layer
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *s, dt=bf: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
+        self.B, self.Tmax = B, Tmax
+        self.Vpad = _round_up(cfg.vocab_size, 128) if cfg.vocab_size <= 1024 else _round_up(cfg.vocab_size, 8)
+        self.cache = [e(B, Tmax * 3 * C) for _ in range(L)]
+        self.x = [e(B, C, dt=f32) for _ in range(2)]
+        self.ln = e(B, C)
+        self.att = e(B, C)
+        self.h = e(B, 4 * C)
+        self.g = e(B, 4 * C)
+        self.stat = e(2, B, dt=f32)
+        self.logits = e(B, self.Vpad)
+
+
 class _GPTStep(torch.autograd.Function):
     """One autograd node for the whole network: forward launches the forward plan, backward the backward plan."""
 
@@ -459,27 +479,89 @@ class GPT(nn.Module):
         flops_per_iter = flops_per_token * T * fwdbwd_per_iter
         return flops_per_iter * (1.0 / dt) / flops_promised
 
-    @torch.no_grad()
-    def generate(self, idx, max_new_tokens, temperature=1.0, top_k=None):
-        """Reference semantics (model.py:305-330): context cropped to block_size, last-position logits, temperature,
-        optional top-k, sample, append.  top_k == 1 (greedy) uses the fused argmax head and a pre-allocated token
-        buffer; other settings sample from the [B, V] last-position logits."""
-        B, T0 = idx.shape
+    def _decode_step(self, st, tokens, t, want_logits):
+        """Position t of every sequence: tokens int64 [B] (any stride-1 view).  Appends this position's q|k|v to the cache
+        and, if want_logits, leaves the next-token logits in st.logits."""
+        cfg = self.config
+        layers = self._layer_tensors()
+        top = self._arena["top"]
+        B, C, H = st.B, cfg.n_embd, cfg.n_head
+        x, y = st.x
+        ops.embed_fwd(tokens, top["wte"][0], top["wpe"][0][t:t + 1], x, 1)
+        for li, lw in enumerate(layers):
+            b = lambda name: None if lw[name] is None else lw[name][0]  # noqa: E731
+            ops.layernorm_fwd(x, lw["ln_1.weight"][0], b("ln_1.bias"), st.ln, st.stat[0], st.stat[1])
+            qkv_t = st.cache[li][:, t * 3 * C:(t + 1) * 3 * C]  # the GEMM writes this position's row of the cache in place
+            ops.gemm(st.ln, lw["attn.c_attn.weight"][1], epilogue=ops.EPI_BF16, out=qkv_t, bias=b("attn.c_attn.bias"), tile_n=128)
+            ops.attn_decode(st.cache[li], st.att, B, st.Tmax, t + 1, H)
+            ops.gemm(st.att, lw["attn.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=y, aux=x, bias=b("attn.c_proj.bias"),
+                     tile_n=128)
+            ops.layernorm_fwd(y, lw["ln_2.weight"][0], b("ln_2.bias"), st.ln, st.stat[0], st.stat[1])
+            ops.gemm(st.ln, lw["mlp.c_fc.weight"][1], epilogue=ops.EPI_GELU, out=st.h, out2=st.g, bias=b("mlp.c_fc.bias"),
+                     tile_n=128)
+            ops.gemm(st.g, lw["mlp.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=x, aux=y, bias=b("mlp.c_proj.bias"),
+                     tile_n=128)
+        if want_logits:
+            lnf_b = None if top["ln_f.bias"] is None else top["ln_f.bias"][0]
+            ops.layernorm_fwd(x, top["ln_f.weight"][0], lnf_b, st.ln, st.stat[0], st.stat[1])
+            ops.gemm(st.ln, top["wte"][1], N=st.Vpad, epilogue=ops.EPI_BF16, out=st.logits, tile_n=128)
+
+    def _sample(self, logits_bf16, out_col, out_stride, temperature, top_k):
         V = self.config.vocab_size
-        out = torch.empty(B, T0 + max_new_tokens, device=idx.device, dtype=torch.int64)
+        if top_k is not None and min(top_k, V) == 1:
+            ops.argmax(logits_bf16, V, out_col, out_stride=out_stride)  # greedy: fused head, no host round trip
+            return
+        logits = logits_bf16[:, :V].float() / temperature
+        if top_k is not None:
+            v, _ = torch.topk(logits, min(top_k, V))
+            logits[logits < v[:, [-1]]] = -float("Inf")
+        probs = torch.softmax(logits, dim=-1)
+        nxt = torch.multinomial(probs, num_samples=1).view(-1)
+        if out_stride == 1:
+            out_col.copy_(nxt)
+        else:
+            out_col[:, 0].copy_(nxt)
+
+    @torch.no_grad()
+    def generate(self, idx, max_new_tokens, temperature=1.0, top_k=None, use_cache=True):
+        """Reference semantics (model.py:305-330): feed the sequence back max_new_tokens times, last-position logits,
+        temperature, optional top-k, sample, append; the context is cropped to block_size.
+
+        While the context window does not slide (position < block_size) each new token costs ONE single-position step over
+        a KV cache instead of the reference's full-context forward; absolute position embeddings make the cache invalid
+        once the window slides, so from there on the context is recomputed per token exactly like the reference.
+        top_k == 1 (greedy) uses the fused argmax head writing straight into the pre-allocated token buffer."""
+        if not idx.is_cuda:
+            raise _C.AbcgptError("GPT.generate: idx must be a CUDA tensor (there is no CPU path)")
+        B, T0 = idx.shape
+        bs = self.config.block_size
+        total = T0 + max_new_tokens
+        out = torch.empty(B, total, device=idx.device, dtype=torch.int64)
         out[:, :T0] = idx
-        for i in range(max_new_tokens):
-            t = T0 + i
-            lo = max(0, t - self.config.block_size)
-            cond = out[:, lo:t].contiguous()
-            bufs = self._forward_plan(cond, None, keep_activations=False)
-            if top_k is not None and min(top_k, V) == 1:
-                ops.argmax(bufs.last_logits, V, out[:, t:], out_stride=out.stride(0))
-                continue
-            logits = bufs.last_logits[:, :V].float() / temperature
-            if top_k is not None:
-                v, _ = torch.topk(logits, min(top_k, V))
-                logits[logits < v[:, [-1]]] = -float("Inf")
-            probs = torch.softmax(logits, dim=-1)
-            out[:, t] = torch.multinomial(probs, num_samples=1).view(-1)
+        was_training = self.training
+        self.eval()
+        try:
+            self._ensure_device_state()
+            t = 0
+            if use_cache and T0 <= bs:
+                key = ("decode", B, bs)
+                if key not in self._bufs:
+                    self._bufs[key] = _DecodeState(self.config, B, bs, idx.device)
+                st = self._bufs[key]
+                col = out.t().contiguous()  # [total, B]: token column t is a contiguous int64 [B]
+                last = min(total - 1, bs)   # positions 0 .. last-1 can be decoded with the cache
+                for t in range(last):
+                    want = t >= T0 - 1
+                    self._decode_step(st, col[t], t, want)
+                    if want:
+                        self._sample(st.logits, col[t + 1], 1, temperature, top_k)
+                out.copy_(col.t())
+                t = last
+            for pos in range(max(t, T0 - 1), total - 1):  # window slides (or cache disabled): reference-style recompute
+                lo = max(0, pos + 1 - bs)
+                cond = out[:, lo:pos + 1].contiguous()
+                bufs = self._forward_plan(cond, None, keep_activations=False)
+                self._sample(bufs.last_logits, out[:, pos + 1:], out.stride(0), temperature, top_k)
+        finally:
+            self.train(was_training)
         return out

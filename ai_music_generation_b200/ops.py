@@ -168,3 +168,8 @@ def argmax(logits, V, out, out_stride=1):
 def colsum_bf16(dy, out):
     M, N = dy.shape
     _call("colsum_bf16", 1, (M, N), _C.lib().abcgpt_colsum_bf16, dy.data_ptr(), dy.stride(0), M, N, out.data_ptr(), _stream())
+
+
+def attn_decode(cache, out, B, Tmax, n_keys, H):
+    _call("attn_decode", 1, (B, n_keys, H), _C.lib().abcgpt_attn_decode, cache.data_ptr(), out.data_ptr(), B, Tmax, n_keys, H,
+          _stream())
