@@ -77,6 +77,10 @@ int abcgpt_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* strea
 int abcgpt_attn_decode(const void* cache, void* out, int B, int Tmax, int n_keys, int H, void* stream) {
   return attn_decode(cache, out, B, Tmax, n_keys, H, S(stream));
 }
+int abcgpt_sample_batch(const void* data, int token_bytes, int64_t n_tokens, const int64_t* ix, int64_t* x, int64_t* y, int B,
+                        int T, void* stream) {
+  return sample_batch(data, token_bytes, n_tokens, ix, x, y, B, T, S(stream));
+}
 int abcgpt_colsum_bf16(const void* dy, int64_t ld, int M, int N, float* out, void* stream) {
   return colsum_bf16(dy, ld, M, N, out, S(stream));
 }

@@ -389,6 +389,25 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
   if (tid < 64) out[static_cast<long long>(b) * C + h * 64 + tid] = __float2bfloat16_rn(part[0][tid] + part[1][tid]);
 }
 
+
+// ---- device-resident token stream (get_batch, train.py:122-144): x[b,:] = data[ix[b] : ix[b]+T], y[b,:] = data[ix[b]+1 : ...+T+1]
+// The whole uint16 (or uint32) corpus lives in HBM (IrishMAN char-level: 61 M tokens = 122 MB); one launch widens B
+// random windows to the int64 ids the model consumes, replacing B host slices + astype + pin + two H2D copies per batch.
+template <typename TokT>
+__global__ void __launch_bounds__(256)
+sample_batch_kernel(const TokT* __restrict__ data, const int64_t* __restrict__ ix, int64_t* __restrict__ x,
+                    int64_t* __restrict__ y, int B, int T) {
+  const long long total = static_cast<long long>(B) * T;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / T), t = static_cast<int>(i - static_cast<long long>(b) * T);
+    const long long o = __ldg(ix + b) + t;
+    const TokT a = __ldg(data + o), c = __ldg(data + o + 1);
+    x[i] = static_cast<int64_t>(a);
+    y[i] = static_cast<int64_t>(c);
+  }
+}
+
 // ---- greedy head (model.py:316-328 with top_k=1) -----------------------------------------------------------
 __global__ void __launch_bounds__(256)
 argmax_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl, int V, int64_t* __restrict__ out,
@@ -538,6 +557,18 @@ int attn_decode(const void* cache, void* out, int B, int Tmax, int n_keys, int H
   attn_decode_kernel<<<B * H, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(cache),
                                                    reinterpret_cast<__nv_bfloat16*>(out), Tmax, n_keys, H, H * 64);
   return launch_status("attn_decode_kernel");
+}
+
+int sample_batch(const void* data, int token_bytes, long long n_tokens, const int64_t* ix, int64_t* x, int64_t* y, int B, int T,
+                 cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(data && ix && x && y && B > 0 && T > 0 && n_tokens > T, "sample_batch: bad arguments");
+  ABCGPT_CHECK_ARG(token_bytes == 2 || token_bytes == 4, "sample_batch: tokens must be uint16 or uint32");
+  const long long total = static_cast<long long>(B) * T;
+  if (token_bytes == 2)
+    sample_batch_kernel<uint16_t><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(data), ix, x, y, B, T);
+  else
+    sample_batch_kernel<uint32_t><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(data), ix, x, y, B, T);
+  return launch_status("sample_batch_kernel");
 }
 
 int colsum_bf16(const void* dy, long long ld, int M, int N, float* out, cudaStream_t stream) {

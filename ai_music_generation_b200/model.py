@@ -111,6 +111,10 @@ class _Buffers:
         self.sum_count = e(2, dt=f32)
         self.loss = e(1, dt=f32)
         self.last_logits = e(B, self.Vpad)
+        self.idx = torch.empty(B, T, device=device, dtype=torch.int64)   # static copies of the inputs: recorded launch plans
+        self.tgt = torch.empty(B, T, device=device, dtype=torch.int64)   # hold raw pointers
+        self.gl = e(1, dt=f32)
+        self.plans = {}
         if keep_activations:
             self.dx = [e(M, C, dt=f32) for _ in range(2)]
             self.dxb = e(M, C)
@@ -140,6 +144,8 @@ class _DecodeState:
         self.g = e(B, 4 * C)
         self.stat = e(2, B, dt=f32)
         self.logits = e(B, self.Vpad)
+        self.col = torch.zeros(Tmax + 1, B, device=device, dtype=torch.int64)  # token column t = contiguous int64 [B]
+        self.plans = {}
 
 
 class _GPTStep(torch.autograd.Function):
@@ -148,6 +154,8 @@ class _GPTStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, model, idx, targets):
         bufs = model._forward_plan(idx, targets, keep_activations=True)
+        if bufs.drop[0] == 0.0 and model._plan_cache_enabled:
+            idx, targets = bufs.idx, bufs.tgt  # the plan staged the inputs into its static buffers
         ctx.model, ctx.bufs, ctx.idx, ctx.targets, ctx.drop = model, bufs, idx, targets, bufs.drop
         B, T = idx.shape
         logits = bufs.logits.view(B, T, -1)[:, :, : model.config.vocab_size]
@@ -183,6 +191,7 @@ class GPT(nn.Module):
         self._bufs = {}
         self._shadow_fresh = False
         self._pending_clip = None
+        self._plan_cache_enabled = True
         self._next_dropout_seed = None  # tests / reproducibility: force the seed of the next training forward
         self.last_dropout_seed = None
         self.require_backward_grad_sync = True
@@ -280,6 +289,10 @@ class GPT(nn.Module):
     def _act_buffers(self, B, T, keep):
         key = (B, T, keep)
         if key not in self._bufs:
+            if not keep:  # inference shapes come and go (generate with a growing context): keep only a few of them
+                stale = [k for k in self._bufs if len(k) == 3 and k[2] is False]
+                for k in stale[:-3]:
+                    del self._bufs[k]
             self._bufs[key] = _Buffers(self.config, B, T, self._arena["flat"].device, keep)
         return self._bufs[key]
 
@@ -307,6 +320,21 @@ class GPT(nn.Module):
         idx = idx.contiguous()
         bufs.drop = (p_drop, keys, seed)
         self.last_dropout_seed = seed
+        # Launch-plan cache: with dropout off every argument of every launch is static (arena views, per-shape buffers,
+        # the stream), so the plan is recorded once and replayed; inputs are staged into static buffers.
+        plan_key = None
+        if p_drop == 0.0 and self._plan_cache_enabled:
+            bufs.idx.copy_(idx)
+            idx = bufs.idx
+            if targets is not None:
+                bufs.tgt.copy_(targets)
+                targets = bufs.tgt
+            plan_key = ("fwd", targets is not None, torch.cuda.current_stream().cuda_stream)
+            plan = bufs.plans.get(plan_key)
+            if plan is not None:
+                ops.replay(plan)
+                return bufs
+            ops.begin_record()
         ops.embed_fwd(idx, top["wte"][0], top["wpe"][0], bufs.x[0], T, drop_p=p_drop, drop_key=keys[0])
         for li, lw in enumerate(layers):
             k = li if keep_activations else 0
@@ -333,6 +361,8 @@ class GPT(nn.Module):
         else:  # last position only (model.py:190): strided A operand, no gather copy
             a = bufs.lnf.view(B, T * C)[:, (T - 1) * C:]
             ops.gemm(a, wte_bf16, M=B, N=bufs.Vpad, K=C, epilogue=ops.EPI_BF16, out=bufs.last_logits)
+        if plan_key is not None:
+            bufs.plans[plan_key] = ops.end_record()
         return bufs
 
     def _backward_plan(self, bufs, idx, targets, grad_loss, drop):
@@ -348,8 +378,18 @@ class GPT(nn.Module):
             a["grad"].zero_()
             for p, o in zip(params, a["offs"]):
                 p.grad = a["grad"][o:o + p.numel()].view(p.shape)
-        gl = grad_loss.to(torch.float32).reshape(1).contiguous()
+        bufs.gl.copy_(grad_loss.reshape(1))
+        gl = bufs.gl
         tflat = targets.contiguous().view(-1)
+        sync = self._grad_sync if (self._grad_sync is not None and self.require_backward_grad_sync) else None
+        plan_key = None
+        if p_drop == 0.0 and self._plan_cache_enabled and targets.data_ptr() == bufs.tgt.data_ptr():
+            plan_key = ("bwd", sync is not None, torch.cuda.current_stream().cuda_stream)
+            plan = bufs.plans.get(plan_key)
+            if plan is not None:
+                ops.replay(plan)
+                return
+            ops.begin_record()
         ops.ce_bwd(bufs.logits, tflat, bufs.sum_count, gl, bufs.dlogits, V)
         wte, wte_bf16, dwte = top["wte"]
         # lm_head: dW[V,C] += dlogits^T lnf ; d(lnf) = dlogits W
@@ -391,11 +431,13 @@ class GPT(nn.Module):
                               lw["ln_1.weight"][2], gw(lw["ln_1.bias"]), drop_p=p_drop if li > 0 else 0.0,
                               drop_key=keys[3 + 3 * (li - 1)] if li > 0 else 0)
             dx, dx_other = dx_other, dx
-            if self._grad_sync is not None and self.require_backward_grad_sync:
-                self._grad_sync.layer_done(li)
+            if sync is not None:
+                ops.record_callback(lambda li=li: sync.layer_done(li))
         ops.embed_bwd(idx.contiguous().view(-1), dx, dwte, top["wpe"][2], T, drop_p=p_drop, drop_key=keys[0])
-        if self._grad_sync is not None and self.require_backward_grad_sync:
-            self._grad_sync.backward_done()
+        if sync is not None:
+            ops.record_callback(sync.backward_done)
+        if plan_key is not None:
+            bufs.plans[plan_key] = ops.end_record()
 
     # ------------------------------------------------------------------------------------------------------
     # reference call surface
@@ -479,9 +521,18 @@ class GPT(nn.Module):
         flops_per_iter = flops_per_token * T * fwdbwd_per_iter
         return flops_per_iter * (1.0 / dt) / flops_promised
 
-    def _decode_step(self, st, tokens, t, want_logits):
-        """Position t of every sequence: tokens int64 [B] (any stride-1 view).  Appends this position's q|k|v to the cache
-        and, if want_logits, leaves the next-token logits in st.logits."""
+    def _decode_step(self, st, t, want_logits, greedy):
+        """Position t of every sequence (tokens st.col[t]).  Appends this position's q|k|v to the cache and, if
+        want_logits, leaves the next-token logits in st.logits (greedy: also writes the argmax into st.col[t + 1]).
+        Every argument is static per (t, flags), so the launch list is recorded once and replayed afterwards."""
+        plan_key = (t, want_logits, greedy, torch.cuda.current_stream().cuda_stream)
+        plan = st.plans.get(plan_key) if self._plan_cache_enabled else None
+        if plan is not None:
+            ops.replay(plan)
+            return
+        if self._plan_cache_enabled:
+            ops.begin_record()
+        tokens = st.col[t]
         cfg = self.config
         layers = self._layer_tensors()
         top = self._arena["top"]
@@ -505,6 +556,10 @@ class GPT(nn.Module):
             lnf_b = None if top["ln_f.bias"] is None else top["ln_f.bias"][0]
             ops.layernorm_fwd(x, top["ln_f.weight"][0], lnf_b, st.ln, st.stat[0], st.stat[1])
             ops.gemm(st.ln, top["wte"][1], N=st.Vpad, epilogue=ops.EPI_BF16, out=st.logits, tile_n=128)
+            if greedy:
+                ops.argmax(st.logits, cfg.vocab_size, st.col[t + 1], out_stride=1)
+        if self._plan_cache_enabled:
+            st.plans[plan_key] = ops.end_record()
 
     def _sample(self, logits_bf16, out_col, out_stride, temperature, top_k):
         V = self.config.vocab_size
@@ -548,14 +603,15 @@ class GPT(nn.Module):
                 if key not in self._bufs:
                     self._bufs[key] = _DecodeState(self.config, B, bs, idx.device)
                 st = self._bufs[key]
-                col = out.t().contiguous()  # [total, B]: token column t is a contiguous int64 [B]
                 last = min(total - 1, bs)   # positions 0 .. last-1 can be decoded with the cache
+                st.col[:T0].copy_(idx.t())
+                greedy = top_k is not None and min(top_k, self.config.vocab_size) == 1
                 for t in range(last):
                     want = t >= T0 - 1
-                    self._decode_step(st, col[t], t, want)
-                    if want:
-                        self._sample(st.logits, col[t + 1], 1, temperature, top_k)
-                out.copy_(col.t())
+                    self._decode_step(st, t, want, greedy and want)
+                    if want and not greedy:
+                        self._sample(st.logits, st.col[t + 1], 1, temperature, top_k)
+                out[:, :last + 1].copy_(st.col[:last + 1].t())
                 t = last
             for pos in range(max(t, T0 - 1), total - 1):  # window slides (or cache disabled): reference-style recompute
                 lo = max(0, pos + 1 - bs)

@@ -21,9 +21,53 @@ def set_profile(sink):
     _PROFILE = sink
 
 
+_RECORD = None    # launch-plan recording: list of (name, nkernels, fn, args) / ("py", callable)
+
+
+def begin_record():
+    """Start recording every C-ABI call (they still execute).  All pointers of a plan are static (arena + per-shape buffers),
+    so a recorded plan can be replayed with ~1 us of Python per launch instead of re-deriving every argument."""
+    global _RECORD
+    _RECORD = []
+
+
+def end_record():
+    global _RECORD
+    plan, _RECORD = _RECORD, None
+    return plan
+
+
+def record_callback(fn):
+    """Interleave a Python callback (e.g. DDP bucket launch) with the recorded launches; runs now and on every replay."""
+    if _RECORD is not None:
+        _RECORD.append(("py", fn))
+    fn()
+
+
+def replay(plan):
+    global LAUNCHES
+    if _PROFILE is not None:  # instrumented pass: fall back to event-bracketed calls
+        for e in plan:
+            if e[0] == "py":
+                e[1]()
+            else:
+                _call(e[0], e[1], e[4], e[2], *e[3])
+        return
+    for e in plan:
+        if e[0] == "py":
+            e[1]()
+            continue
+        LAUNCHES += e[1]
+        rc = e[2](*e[3])
+        if rc != 0:
+            _C.check(rc, e[0])
+
+
 def _call(name, nkernels, meta, fn, *args):
     global LAUNCHES
     LAUNCHES += nkernels
+    if _RECORD is not None:
+        _RECORD.append((name, nkernels, fn, args, meta))
     if _PROFILE is None:
         rc = fn(*args)
     else:
@@ -173,3 +217,9 @@ def colsum_bf16(dy, out):
 def attn_decode(cache, out, B, Tmax, n_keys, H):
     _call("attn_decode", 1, (B, n_keys, H), _C.lib().abcgpt_attn_decode, cache.data_ptr(), out.data_ptr(), B, Tmax, n_keys, H,
           _stream())
+
+
+def sample_batch(data, ix, x, y):
+    B, T = x.shape
+    _call("sample_batch", 1, (B, T), _C.lib().abcgpt_sample_batch, data.data_ptr(), data.element_size(), data.numel(),
+          ix.data_ptr(), x.data_ptr(), y.data_ptr(), B, T, _stream())

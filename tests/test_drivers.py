@@ -68,3 +68,28 @@ def test_train_then_sample_end_to_end(tmp_path, cuda_device):
     assert outs == ["sample_0.abc", "sample_1.abc", "sample_2.abc"]
     texts = [open(tmp_path / "out-test" / "samples" / o).read() for o in outs]
     assert texts[0].startswith("X:0\n") and texts[0][4:] == texts[1][4:]   # greedy: identical continuations
+
+
+@pytest.mark.gpu
+def test_device_token_stream_is_bit_exact_with_reference_get_batch(tmp_path, cuda_device):
+    """Integer path: the device gather must reproduce the reference's get_batch (train.py:136-138) bit for bit, for uint16
+    and uint32 corpora, given the same torch seed."""
+    import torch
+    from ai_music_generation_b200 import DeviceTokenStream
+    rng = np.random.default_rng(0)
+    for wide, dtype in ((False, np.uint16), (True, np.uint32)):
+        d = tmp_path / ("w" if wide else "n")
+        d.mkdir()
+        data = rng.integers(0, 65535 if not wide else 98465, size=50_000).astype(dtype)
+        data.tofile(d / "train.bin")
+        data[:5000].tofile(d / "val.bin")
+        B, T = 16, 256
+        stream = DeviceTokenStream(str(d), T, B, cuda_device, wide_tokens=wide)
+        for split, arr in (("train", data), ("val", data[:5000])):
+            torch.manual_seed(123)
+            x, y = stream.get(split)
+            torch.manual_seed(123)
+            ix = torch.randint(len(arr) - T, (B,))
+            xr = torch.stack([torch.from_numpy(arr[i:i + T].astype(np.int64)) for i in ix])
+            yr = torch.stack([torch.from_numpy(arr[i + 1:i + 1 + T].astype(np.int64)) for i in ix])
+            assert torch.equal(x.cpu(), xr) and torch.equal(y.cpu(), yr)

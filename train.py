@@ -25,7 +25,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ai_music_generation_b200 import DDP, GPT, GPTConfig
+from ai_music_generation_b200 import DDP, GPT, DeviceTokenStream, GPTConfig
 from configurator import load_settings
 
 DEFAULTS = dict(
@@ -35,6 +35,7 @@ DEFAULTS = dict(
     bias=False, learning_rate=6e-4, max_iters=600000, weight_decay=1e-1, beta1=0.9, beta2=0.95, grad_clip=1.0,
     decay_lr=True, warmup_iters=2000, lr_decay_iters=600000, min_lr=6e-5, backend="nccl", device="cuda",
     dtype="bfloat16", compile=False,
+    device_loader=True,  # new knob: keep train.bin / val.bin in HBM and gather batches with one kernel (same batches as the host loader)
 )
 
 
@@ -85,8 +86,9 @@ def main():
     torch.manual_seed(1337 + rank)
 
     data_dir = os.path.join("data", s["dataset"])
-    stream = TokenStream(data_dir, s["block_size"], s["batch_size"], device,
-                         wide_tokens=s["out_dir"] == "out-irishman-whitespace")  # the reference's uint32 special case
+    Loader = DeviceTokenStream if s["device_loader"] else TokenStream
+    stream = Loader(data_dir, s["block_size"], s["batch_size"], device,
+                    wide_tokens=s["out_dir"] == "out-irishman-whitespace")  # the reference's uint32 special case
     vocab = None
     meta_path = os.path.join(data_dir, "meta.pkl")
     if os.path.exists(meta_path):
