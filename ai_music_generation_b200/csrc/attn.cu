@@ -227,8 +227,7 @@ __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, u
 struct FwdSmem {
   static constexpr int Q = 0;                 // 128 x 64 bf16
   static constexpr int KV = 16384;            // 3 stages x (K 64x64 | V 64x64)
-  static constexpr int P = 16384 + 3 * 16384; // 2 buffers of 128 x 64 bf16
-  static constexpr int BAR = P + 2 * 16384;
+  static constexpr int BAR = 16384 + 3 * 16384;  // P never touches shared memory: it is written back into TMEM
   static constexpr int TOTAL = BAR + 256 + 1024;
 };
 constexpr float kRescaleThreshold = 64.0f;  // log2 units
@@ -369,7 +368,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(128, 64, 0, 1);
       const uint32_t sQ = ptx::smem_u32(smem + FwdSmem::Q);
       const uint32_t sKV = ptx::smem_u32(smem + FwdSmem::KV);
-      const uint32_t sP = ptx::smem_u32(smem + FwdSmem::P);
       ptx::mbar_wait(q_full, 0, 12);
       ptx::mbar_wait(&kv_full[0], 0, 13);
       ptx::tc_fence_after();
@@ -390,9 +388,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1, 15);
         ptx::tc_fence_after();
         const uint32_t sV = sKV + (j % 3) * 16384 + 8192;
-        const uint32_t sPj = sP + (j & 1) * 16384;
+        const uint32_t tP = tmem_base + (j & 1) * 64;  // bf16 P (32 packed columns) written over the consumed S tile
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_O, desc_k(sPj, k), desc_mn(sV, k), idesc_o, (j > 0 || k > 0));
+        for (int k = 0; k < 4; ++k) ptx::umma_ts(tm_O, tP + 8 * k, desc_mn(sV, k), idesc_o, (j > 0 || k > 0));
         ptx::umma_commit(&kv_empty[j % 3]);
         ptx::umma_commit(&p_empty[j & 1]);
       }
@@ -403,7 +401,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t sP = ptx::smem_u32(smem + FwdSmem::P);
     const int r0 = qt * 128 + quarter * 32;  // first query row of this warp (relative to the sequence)
     float m_ref = 0.f, l = 0.f;
     const uint32_t drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(blockIdx.y * T + qt * 128 + r));
@@ -458,11 +455,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       l += rowsum;
       ATTN_STAMP(2);
-      if (j >= 2) ptx::mbar_wait(&p_empty[bsel], ((j >> 1) - 1) & 1, 18);  // P V of tile j-2 has finished reading this buffer
       ATTN_STAMP(3);
-      st_slab32(sP + bsel * 16384, r, 0, pk);
-      st_slab32(sP + bsel * 16384, r, 1, pk + 16);
-      ptx::fence_proxy_async_smem();
+      // P (64 key columns = 32 packed words) overwrites the first half of this tile's S buffer; the tensor pipe runs in
+      // issue order, so S_{j+2} cannot overwrite it before P V of this tile has consumed it
+      ptx::tmem_st16(tm_s, pk);
+      ptx::tmem_st16(tm_s + 16, pk + 16);
+      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_full[bsel]);
       ATTN_STAMP(4);
@@ -534,8 +532,7 @@ struct DqSmem {
   static constexpr int Q = 0;         // 128 x 64
   static constexpr int DO = 16384;    // 128 x 64
   static constexpr int KV = 32768;    // kRing stages x (K 64x64 | V 64x64)
-  static constexpr int DS = KV + kRing * 16384;  // 2 buffers x 128 x 64
-  static constexpr int BAR = DS + 2 * 16384;
+  static constexpr int BAR = KV + kRing * 16384;  // dS never touches shared memory: it is written back into TMEM
   static constexpr int TOTAL = BAR + 256 + 1024;
 };
 
@@ -554,10 +551,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   uint64_t* kv_full = bars + 1;                 // [kRing]
   uint64_t* kv_empty = kv_full + kRing;         // [kRing]
   uint64_t* s_full = kv_empty + kRing;          // [kSBuf]
-  uint64_t* s_free = s_full + kSBuf;            // [kSBuf]
+  uint64_t* s_free = s_full + kSBuf;            // [kSBuf] committed after the dQ MMA that read dS out of this buffer
   uint64_t* ds_full = s_free + kSBuf;           // [2]
-  uint64_t* dq_done = ds_full + 2;              // [2]
-  uint64_t* all_done = dq_done + 2;  // dedicated: a parity wait is only meaningful to a thread that followed every phase
+  uint64_t* all_done = ds_full + 2;  // dedicated: a parity wait is only meaningful to a thread that followed every phase
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -578,12 +574,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     }
     for (int s = 0; s < kSBuf; ++s) {
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&s_free[s], 128);
+      ptx::mbar_init(&s_free[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&ds_full[s], 128);
-      ptx::mbar_init(&dq_done[s], 1);
-    }
+    for (int s = 0; s < 2; ++s) ptx::mbar_init(&ds_full[s], 128);
     ptx::mbar_init(all_done, 1);
     ptx::fence_mbar_init();
   }
@@ -623,7 +616,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
       ptx::mbar_wait(qdo_full, 0, 21);
       for (int j = 0; j < num_kv; ++j) {
         ptx::mbar_wait(&kv_full[j % kRing], (j / kRing) & 1, 22);
-        if (j >= kSBuf) ptx::mbar_wait(&s_free[j % kSBuf], ((j / kSBuf) - 1) & 1, 23);  // step j-3 has left this buffer
+        if (j >= kSBuf) ptx::mbar_wait(&s_free[j % kSBuf], ((j / kSBuf) - 1) & 1, 23);  // the dQ MMA of step j-3 has read its dS
         ptx::tc_fence_after();
         const uint64_t dK = dKV0 + static_cast<uint64_t>((j % kRing) * (16384 >> 4)), dV = dK + (8192 >> 4);
         const uint32_t tS = tmem_base + (j % kSBuf) * 128;
@@ -639,17 +632,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     // ---- accumulating MMAs: dQ += dS_j K_j
     if (lane == 0) {
       constexpr uint32_t idesc_dq = ptx::umma_idesc_bf16(128, 64, 0, 1);
-      const uint64_t dDS0 = desc_k(ptx::smem_u32(smem + DqSmem::DS), 0);
       const uint64_t dKmn0 = desc_mn(ptx::smem_u32(smem + DqSmem::KV), 0);
       for (int j = 0; j < num_kv; ++j) {
         ptx::mbar_wait(&ds_full[j & 1], (j >> 1) & 1, 23);
         ptx::tc_fence_after();
-        const uint64_t dDS = dDS0 + static_cast<uint64_t>((j & 1) * (16384 >> 4));
+        // A = dS (bf16 pairs, 32 columns) sits in the first columns of this step's score buffer
+        const uint32_t tA = tmem_base + (j % kSBuf) * 128;
         const uint64_t dK = dKmn0 + static_cast<uint64_t>((j % kRing) * (16384 >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dQ, dDS + 2 * k, dK + (2048 >> 4) * k, idesc_dq, (j > 0 || k > 0));
+        for (int k = 0; k < 4; ++k) ptx::umma_ts(tm_dQ, tA + 8 * k, dK + (2048 >> 4) * k, idesc_dq, (j > 0 || k > 0));
         ptx::umma_commit(&kv_empty[j % kRing]);  // S_j / dP_j (other issuer) completed before ds_full(j) could complete
-        ptx::umma_commit(&dq_done[j & 1]);
+        ptx::umma_commit(&s_free[j % kSBuf]);    // the score buffer (now holding dS) may be overwritten
       }
       ptx::umma_commit(all_done);
     }
@@ -659,7 +652,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t sDS = ptx::smem_u32(smem + DqSmem::DS) + g * 16384;
     const int t = qt * 128 + r;
     const bool valid = t < T;
     const long long stat_idx = (static_cast<long long>(b) * H + h) * T + t;
@@ -673,23 +665,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
       ptx::mbar_wait(&s_full[j % kSBuf], (j / kSBuf) & 1, 24);
       ptx::tc_fence_after();
       DQ_STAMP(1);
-      uint32_t pk[32];
+      const uint32_t tbuf = tmem_base + lane_off + (j % kSBuf) * 128;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int c0 = j * 64 + c * 32;
-        const uint32_t ta_s = tmem_base + lane_off + (j % kSBuf) * 128 + c * 32, ta_dp = ta_s + 64;
-        if (c0 + 31 <= r0) dq_chunk<kFull, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16, dcfg, drop_rk, c0);
-        else if (c0 > r0 + 31) dq_chunk<kMasked, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16, dcfg, drop_rk, c0);
-        else dq_chunk<kDiag, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk + c * 16, dcfg, drop_rk, c0);
+        const uint32_t ta_s = tbuf + c * 32, ta_dp = ta_s + 64;
+        uint32_t pk[16];
+        if (c0 + 31 <= r0) dq_chunk<kFull, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk, dcfg, drop_rk, c0);
+        else if (c0 > r0 + 31) dq_chunk<kMasked, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk, dcfg, drop_rk, c0);
+        else dq_chunk<kDiag, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk, dcfg, drop_rk, c0);
+        // dS chunk c (32 key columns = 16 packed words) overwrites score columns that this thread has already consumed
+        ptx::tmem_st16(tbuf + c * 16, pk);
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&s_free[j % kSBuf]);  // both score tiles of this step are in registers
       DQ_STAMP(2);
-      if (use > 0) ptx::mbar_wait(&dq_done[g], (use - 1) & 1, 25);  // the dQ MMA of step j-2 has finished reading this dS buffer
       DQ_STAMP(3);
-      st_slab32(sDS, r, 0, pk);
-      st_slab32(sDS, r, 1, pk + 16);
-      ptx::fence_proxy_async_smem();
+      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&ds_full[g]);
       DQ_STAMP(4);
@@ -723,9 +713,8 @@ struct DkvSmem {
   static constexpr int K = 0;          // 128 x 64
   static constexpr int V = 16384;      // 128 x 64
   static constexpr int QDO = 32768;    // kRing stages x (Q 64x64 | dO 64x64)
-  static constexpr int PT = QDO + kRing * 16384;  // 2 buffers x 128 x 64   P^T
-  static constexpr int DST = PT + 2 * 16384;      // 2 buffers x 128 x 64   dS^T
-  static constexpr int STAT = DST + 2 * 16384;    // 2 groups x 2 buffers x (-lse2[64] | -delta8[64] | dropout row key[64])
+  // P^T and dS^T never touch shared memory: they are written back into TMEM and consumed as the A operand from there
+  static constexpr int STAT = QDO + kRing * 16384;  // 2 groups x 2 buffers x (-lse2[64] | -delta8[64] | dropout row key[64])
   static constexpr int BAR = STAT + 3072;
   static constexpr int TOTAL = BAR + 256 + 1024;
 };
@@ -745,10 +734,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   uint64_t* qdo_full = bars + 1;                // [kRing]
   uint64_t* qdo_empty = qdo_full + kRing;       // [kRing]
   uint64_t* s_full = qdo_empty + kRing;         // [kSBuf]
-  uint64_t* s_free = s_full + kSBuf;            // [kSBuf]
+  uint64_t* s_free = s_full + kSBuf;            // [kSBuf] committed after the dV / dK MMAs that read P^T / dS^T out of the buffer
   uint64_t* pds_full = s_free + kSBuf;          // [2]
-  uint64_t* pds_empty = pds_full + 2;           // [2]
-  uint64_t* all_done = pds_empty + 2;
+  uint64_t* all_done = pds_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
   float* stat = reinterpret_cast<float*>(smem + DkvSmem::STAT);
 
@@ -769,12 +757,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     }
     for (int s = 0; s < kSBuf; ++s) {
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&s_free[s], 128);
+      ptx::mbar_init(&s_free[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&pds_full[s], 128);
-      ptx::mbar_init(&pds_empty[s], 1);
-    }
+    for (int s = 0; s < 2; ++s) ptx::mbar_init(&pds_full[s], 128);
     ptx::mbar_init(all_done, 1);
     ptx::fence_mbar_init();
   }
@@ -813,7 +798,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       ptx::mbar_wait(kv_full, 0, 31);
       for (int n = 0; n < nq; ++n) {
         ptx::mbar_wait(&qdo_full[n % kRing], (n / kRing) & 1, 32);
-        if (n >= kSBuf) ptx::mbar_wait(&s_free[n % kSBuf], ((n / kSBuf) - 1) & 1, 33);  // step n-3 has left this buffer
+        if (n >= kSBuf) ptx::mbar_wait(&s_free[n % kSBuf], ((n / kSBuf) - 1) & 1, 33);  // dV / dK of step n-3 have read it
         ptx::tc_fence_after();
         const uint64_t dQ = dQDO0 + static_cast<uint64_t>((n % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
         const uint32_t tS = tmem_base + (n % kSBuf) * 128;
@@ -829,19 +814,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     // ---- accumulating MMAs: dV += P^T_n dO_n, dK += dS^T_n Q_n
     if (lane == 0) {
       constexpr uint32_t idesc_g = ptx::umma_idesc_bf16(128, 64, 0, 1);
-      const uint64_t dPT0 = desc_k(ptx::smem_u32(smem + DkvSmem::PT), 0), dDST0 = desc_k(ptx::smem_u32(smem + DkvSmem::DST), 0);
       const uint64_t dQmn0 = desc_mn(ptx::smem_u32(smem + DkvSmem::QDO), 0);
       for (int n = 0; n < nq; ++n) {
         ptx::mbar_wait(&pds_full[n & 1], (n >> 1) & 1, 33);
         ptx::tc_fence_after();
-        const uint64_t boff = static_cast<uint64_t>((n & 1) * (16384 >> 4));
+        const uint32_t tP = tmem_base + (n % kSBuf) * 128, tDS = tP + 64;  // bf16 pairs written over the consumed scores
         const uint64_t dQ = dQmn0 + static_cast<uint64_t>((n % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dV, dPT0 + boff + 2 * k, dDO + (2048 >> 4) * k, idesc_g, (n > 0 || k > 0));
+        for (int k = 0; k < 4; ++k) ptx::umma_ts(tm_dV, tP + 8 * k, dDO + (2048 >> 4) * k, idesc_g, (n > 0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tm_dK, dDST0 + boff + 2 * k, dQ + (2048 >> 4) * k, idesc_g, (n > 0 || k > 0));
+        for (int k = 0; k < 4; ++k) ptx::umma_ts(tm_dK, tDS + 8 * k, dQ + (2048 >> 4) * k, idesc_g, (n > 0 || k > 0));
         ptx::umma_commit(&qdo_empty[n % kRing]);
-        ptx::umma_commit(&pds_empty[n & 1]);
+        ptx::umma_commit(&s_free[n % kSBuf]);
       }
       ptx::umma_commit(all_done);
     }
@@ -852,8 +836,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     const int r = quarter * 32 + lane;      // key row inside the tile
     const int tid = (warp - 2 - 4 * g) * 32 + lane;  // 0..127 within the group
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t sPT = ptx::smem_u32(smem + DkvSmem::PT) + g * 16384;
-    const uint32_t sDST = ptx::smem_u32(smem + DkvSmem::DST) + g * 16384;
     const int kv_t = kt * 128 + r;
     const bool valid = kv_t < T;
     const long long stat_base = (static_cast<long long>(b) * H + h) * T;
@@ -875,26 +857,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       ptx::mbar_wait(&s_full[n % kSBuf], (n / kSBuf) & 1, 34);
       ptx::tc_fence_after();
       DKV_STAMP(1);
-      uint32_t pk_p[32], pk_ds[32];
+      const uint32_t tbuf = tmem_base + lane_off + (n % kSBuf) * 128;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int c0 = q0 + c * 32;
-        const uint32_t ta_s = tmem_base + lane_off + (n % kSBuf) * 128 + c * 32, ta_dp = ta_s + 64;
+        const uint32_t ta_s = tbuf + c * 32, ta_dp = ta_s + 64;
         const uint32_t l2 = ptx::smem_u32(st_lse) + c * 128, d8 = l2 + 256, rkeys = l2 + 512;
-        if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16, dcfg, rkeys);
-        else if (c0 + 31 < r0 || c0 >= T) dkv_chunk<kMasked, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16, dcfg, rkeys);
-        else dkv_chunk<kDiag, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p + c * 16, pk_ds + c * 16, dcfg, rkeys);
+        uint32_t pk_p[16], pk_ds[16];
+        if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p, pk_ds, dcfg, rkeys);
+        else if (c0 + 31 < r0 || c0 >= T) dkv_chunk<kMasked, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p, pk_ds, dcfg, rkeys);
+        else dkv_chunk<kDiag, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p, pk_ds, dcfg, rkeys);
+        // P^T / dS^T chunk c (32 query columns = 16 packed words each) overwrite score columns already consumed
+        ptx::tmem_st16(tbuf + c * 16, pk_p);
+        ptx::tmem_st16(tbuf + 64 + c * 16, pk_ds);
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&s_free[n % kSBuf]);
       DKV_STAMP(2);
-      if (use > 0) ptx::mbar_wait(&pds_empty[g], (use - 1) & 1, 35);
       DKV_STAMP(3);
-      st_slab32(sPT, r, 0, pk_p);
-      st_slab32(sPT, r, 1, pk_p + 16);
-      st_slab32(sDST, r, 0, pk_ds);
-      st_slab32(sDST, r, 1, pk_ds + 16);
-      ptx::fence_proxy_async_smem();
+      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&pds_full[g]);
       DKV_STAMP(4);
