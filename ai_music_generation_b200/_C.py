@@ -41,6 +41,7 @@ _SIGNATURES = {
     "abcgpt_colsum_bf16": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "abcgpt_debug_gemm_stats": (c_int, [_P]),
     "abcgpt_debug_attn_trace": (c_int, [_P]),
+    "abcgpt_debug_attn_cta_trace": (c_int, [_P]),
     "abcgpt_argmax": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P]),
 }
 

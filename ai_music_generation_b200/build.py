@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libabcgpt.so")
 SOURCES = ["common.cu", "gemm.cu", "attn.cu", "layernorm.cu", "elementwise.cu", "api.cu"]
-HEADERS = ["common.h", "kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "abcgpt.h")]
+HEADERS = ["common.h", "kernels.h", "ptx.cuh", "dropout.cuh", os.path.join("..", "..", "include", "abcgpt.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -4,7 +4,7 @@
 #include "kernels.h"
 
 using namespace abcgpt;
-namespace abcgpt { extern unsigned long long* g_gemm_stats; extern long long* g_attn_trace; }
+namespace abcgpt { extern unsigned long long* g_gemm_stats; extern long long* g_attn_trace; extern long long* g_attn_cta_trace; }
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
 
@@ -91,6 +91,12 @@ int abcgpt_argmax(const void* logits, int64_t ldl, int V, int64_t* out, int64_t 
 /* debug: device pointer to 8 uint64 cycle counters filled by subsequent GEMM launches (NULL disables) */
 int abcgpt_debug_gemm_stats(void* device_counters) {
   abcgpt::g_gemm_stats = reinterpret_cast<unsigned long long*>(device_counters);
+  return 0;
+}
+
+/* debug: 3 x (CTAs of one attention launch) x 4 int64 {start ns, end ns, SM id, steps}: forward, dK/dV, dQ kernels */
+int abcgpt_debug_attn_cta_trace(void* device_records) {
+  abcgpt::g_attn_cta_trace = reinterpret_cast<long long*>(device_records);
   return 0;
 }
 

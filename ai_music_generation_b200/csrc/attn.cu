@@ -3,13 +3,14 @@
 // split / merge copies at model.py:56-59,72: the kernels read q|k|v straight out of the packed c_attn output
 // [B*T, 3C] through one TMA tensor map (column offset selects q/k/v and the head) and write [B*T, C] directly.
 //
-//   attn_fwd_kernel   one CTA per (128 query rows, batch*head); K/V streamed in 128-row tiles
-//                     S = Q K^T (UMMA 128x128x64) -> TMEM -> online softmax, one thread per query row
-//                     -> P (bf16) into 128B-swizzled smem -> O_tile = P V (UMMA 128x64x128) -> TMEM -> registers
-//   attn_bwd_dq_kernel    one CTA per 128 query rows, K/V in 64-row tiles:   S, dP -> dS -> dQ += dS K   (TMEM acc)
-//   attn_bwd_dkv_kernel   one CTA per 128 key rows,  Q/dO in 64-row tiles:  S^T, dP^T -> P^T, dS^T -> dV += P^T dO,
+// Work item = (128-row tile, batch*head); all three kernels are persistent over a static item schedule.
+//   attn_fwd_kernel       item = 128 query rows; K/V streamed in 64-row tiles
+//                         S = Q K^T (UMMA 128x64x64) -> TMEM -> softmax, one thread per query row -> bf16 P back into
+//                         TMEM -> O += P V (UMMA, A operand from TMEM) accumulated in TMEM -> registers at item end
+//   attn_bwd_dq_kernel    item = 128 query rows, K/V in 64-row tiles:   S, dP -> dS -> dQ += dS K   (TMEM acc)
+//   attn_bwd_dkv_kernel   item = 128 key rows,  Q/dO in 64-row tiles:  S^T, dP^T -> P^T, dS^T -> dV += P^T dO,
 //                         dK += dS^T Q (TMEM acc).  Two kernels instead of atomics on dQ: deterministic gradients.
-// Two CTAs are co-resident per SM so that one CTA's softmax (MUFU-bound) overlaps the other's MMAs.
+// The forward runs two CTAs per SM so that one CTA's softmax (MUFU-bound) overlaps the other's MMAs.
 #include "common.h"
 #include "dropout.cuh"
 #include "kernels.h"
@@ -18,6 +19,7 @@
 namespace abcgpt {
 
 long long* g_attn_trace = nullptr;  // debug only (abcgpt_debug_attn_trace): per-phase clock64 stamps of one CTA
+long long* g_attn_cta_trace = nullptr;  // debug only (abcgpt_debug_attn_cta_trace): {start ns, end ns, SM id, steps} per CTA
 
 namespace {
 
@@ -27,6 +29,20 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kScale = 0.125f;  // 1/sqrt(64)
 constexpr float kSl2 = kScale * kLog2e;
 constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 one thread per tile row
+
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void cta_trace_write(long long* cta_trace, long long t0, int steps) {
+  if (cta_trace != nullptr) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    long long* o = cta_trace + 4ll * blockIdx.x;
+    o[0] = t0; o[1] = globaltimer_ns(); o[2] = smid; o[3] = steps;
+  }
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -215,21 +231,6 @@ __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, u
   }
 }
 
-// ======================================================================================================
-// forward
-// ======================================================================================================
-// 128 query rows per CTA, K/V streamed in 64-row tiles through a 3-stage ring.  The score tile S (128 x 64 fp32) is
-// double-buffered in TMEM so the tensor core computes S_{j+1} while the softmax threads work on S_j; P is
-// double-buffered in shared memory; O accumulates in TMEM across all tiles (tcgen05.mma accumulate), so the softmax
-// threads never touch O until the end.  That needs a per-row reference exponent that is NOT the running max:
-// m_ref is the true max of the first tile and is only raised (with an in-TMEM rescale of O) when a later tile exceeds
-// it by more than 2^64 -- exact in floating point, because a common power-of-two factor cancels in O / l.
-struct FwdSmem {
-  static constexpr int Q = 0;                 // 128 x 64 bf16
-  static constexpr int KV = 16384;            // 3 stages x (K 64x64 | V 64x64)
-  static constexpr int BAR = 16384 + 3 * 16384;  // P never touches shared memory: it is written back into TMEM
-  static constexpr int TOTAL = BAR + 256 + 1024;
-};
 constexpr float kRescaleThreshold = 64.0f;  // log2 units
 
 // p = 2^(s*sl2 - m_ref) for one 32-column chunk, also tracks the raw row max; MODE as for the other chunk helpers
@@ -295,46 +296,82 @@ __device__ __forceinline__ void fwd_tile(uint32_t tm_s, int lane, int cls0, int 
   }
 }
 
+// ======================================================================================================
+// persistent scheduling
+// ======================================================================================================
+// All three tensor-core kernels are PERSISTENT: a fixed grid (one or two CTAs per SM) walks a static list of work
+// items, one item = one (128-row tile, batch*head) pair.  Measured before (one CTA per item): every CTA paid ~2.3-3.6 us
+// of un-overlapped prologue / epilogue plus ~1.5 us of launch gap against ~5 us of useful steps.  Now the producer,
+// MMA and compute roles each run their own loop over the item list with free-running step counters, so the loads and
+// score MMAs of the next item start while the current item's accumulators are still being drained.
+// Items are numbered heaviest tile first (all batch*heads of the heaviest tile, then the next one, ...) and dealt to
+// the CTAs in boustrophedon passes: a static schedule whose per-CTA load differs by <= 1-2 % at the cfg3 shape.
+__device__ __forceinline__ int sched_item(int k, int nitems) {
+  const int G = gridDim.x, c = blockIdx.x;
+  const int i = k * G + ((k & 1) ? G - 1 - c : c);
+  return i < nitems ? i : -1;
+}
+
+// ======================================================================================================
+// forward
+// ======================================================================================================
+// 128 query rows per item, K/V streamed in 64-row tiles through a ring.  The score tile S (128 x 64 fp32) is
+// double-buffered in TMEM so the tensor core computes S_{j+1} while the softmax threads work on S_j; the bf16 P tile is
+// written back over the consumed S tile and read by the P V MMA straight from TMEM; O accumulates in TMEM across all
+// tiles of an item (two O buffers: the epilogue of item i overlaps the MMAs of item i+1).  Accumulating O in TMEM
+// needs a per-row reference exponent that is NOT the running max: m_ref is the true max of the first tile and is
+// only raised (with an in-TMEM rescale of O) when a later tile exceeds it by more than 2^64 -- exact in floating
+// point, because a common power-of-two factor cancels in O / l.
+constexpr int kFwdRing = 4;
+struct FwdSmem {
+  static constexpr int Q = 0;                       // 2 items x (128 x 64 bf16)
+  static constexpr int KV = 32768;                  // kFwdRing stages x (K 64x64 | V 64x64)
+  static constexpr int BAR = KV + kFwdRing * 16384;
+  static constexpr int TOTAL = BAR + 256 + 1024;
+};
+
 template <bool DROP>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int C, long long* trace,
-                const DropCfg dcfg) {
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int C, int BH, int nitems,
+                long long* trace, const DropCfg dcfg, long long* cta_trace) {
+  const long long cta_t0 = cta_trace ? globaltimer_ns() : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [3]
-  uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;     // [2]
-  uint64_t* p_full = bars + 9;     // [2]
-  uint64_t* p_empty = bars + 11;   // [2]
-  uint64_t* o_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_full = bars + 0;                   // [2]
+  uint64_t* q_empty = bars + 2;                  // [2]
+  uint64_t* kv_full = bars + 4;                  // [kFwdRing]
+  uint64_t* kv_empty = kv_full + kFwdRing;       // [kFwdRing]
+  uint64_t* s_full = kv_empty + kFwdRing;        // [2]
+  uint64_t* p_full = s_full + 2;                 // [2]
+  uint64_t* p_empty = p_full + 2;                // [2]
+  uint64_t* o_full = p_empty + 2;                // [2]
+  uint64_t* o_free = o_full + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;
-  const int b = blockIdx.y / H, h = blockIdx.y % H;
-  const int row0 = b * T + qt * 128;
-  const int kv_end = min(T, qt * 128 + 128);
-  const int num_kv = (kv_end + 63) / 64;
-  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
-#define ATTN_STAMP(k) do { if (tr) trace[j * 8 + (k)] = clock64(); } while (0)
+  const int nqt = (T + 127) / 128;
+  const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+  int total_steps = 0;
+#define ATTN_STAMP(k) do { if (tr && item_k == 0 && j < 16) trace[j * 8 + (k)] = clock64(); } while (0)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmKV);
-    ptx::mbar_init(q_full, 1);
-    for (int s = 0; s < 3; ++s) {
-      ptx::mbar_init(&kv_full[s], 1);
-      ptx::mbar_init(&kv_empty[s], 1);
-    }
     for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&q_full[s], 1);
+      ptx::mbar_init(&q_empty[s], 1);
       ptx::mbar_init(&s_full[s], 1);
       ptx::mbar_init(&p_full[s], 128);
       ptx::mbar_init(&p_empty[s], 1);
+      ptx::mbar_init(&o_full[s], 1);
+      ptx::mbar_init(&o_free[s], 128);
     }
-    ptx::mbar_init(o_full, 1);
+    for (int s = 0; s < kFwdRing; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -344,21 +381,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_O = tmem_base + 128;  // S buffers at columns [0,64) and [64,128)
+  const uint32_t tmem_base = *tmem_slot;  // S buffers at columns [0,64) and [64,128); O buffers at [128,192) and [192,256)
+
+  // number of 64-row K/V tiles of an item
+  auto tiles_of = [&](int it) {
+    const int qt = nqt - 1 - it / BH;
+    return (min(T, qt * 128 + 128) + 63) / 64;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(q_full, 16384);
-      ptx::tma_load_2d(smem + FwdSmem::Q, &tmQ, q_full, h * HS, row0);
-      for (int j = 0; j < num_kv; ++j) {
-        const int st = j % 3;
-        const uint32_t ph = (j / 3) & 1;
-        ptx::mbar_wait(&kv_empty[st], ph ^ 1, 10);
-        ptx::mbar_expect_tx(&kv_full[st], 16384);
-        uint8_t* dst = smem + FwdSmem::KV + st * 16384;
-        ptx::tma_load_2d(dst, &tmKV, &kv_full[st], C + h * HS, b * T + j * 64);
-        ptx::tma_load_2d(dst + 8192, &tmKV, &kv_full[st], 2 * C + h * HS, b * T + j * 64);
+      int gt = 0;
+      for (int item_k = 0;; ++item_k) {
+        const int it = sched_item(item_k, nitems);
+        if (it < 0) break;
+        const int qt = nqt - 1 - it / BH, bh = it % BH, b = bh / H, h = bh % H;
+        const int num_kv = tiles_of(it);
+        const int qb = item_k & 1;
+        ptx::mbar_wait(&q_empty[qb], ((item_k >> 1) & 1) ^ 1, 10);
+        ptx::mbar_expect_tx(&q_full[qb], 16384);
+        ptx::tma_load_2d(smem + FwdSmem::Q + qb * 16384, &tmQ, &q_full[qb], h * HS, b * T + qt * 128);
+        for (int j = 0; j < num_kv; ++j, ++gt) {
+          const int st = gt % kFwdRing;
+          ptx::mbar_wait(&kv_empty[st], ((gt / kFwdRing) & 1) ^ 1, 11);
+          ptx::mbar_expect_tx(&kv_full[st], 16384);
+          uint8_t* dst = smem + FwdSmem::KV + st * 16384;
+          ptx::tma_load_2d(dst, &tmKV, &kv_full[st], C + h * HS, b * T + j * 64);
+          ptx::tma_load_2d(dst + 8192, &tmKV, &kv_full[st], 2 * C + h * HS, b * T + j * 64);
+        }
       }
     }
     __syncwarp();
@@ -368,131 +418,189 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(128, 64, 0, 1);
       const uint32_t sQ = ptx::smem_u32(smem + FwdSmem::Q);
       const uint32_t sKV = ptx::smem_u32(smem + FwdSmem::KV);
-      ptx::mbar_wait(q_full, 0, 12);
-      ptx::mbar_wait(&kv_full[0], 0, 13);
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ptx::umma_ss(tmem_base, desc_k(sQ, k), desc_k(sKV, k), idesc_s, k > 0);
-      ptx::umma_commit(&s_full[0]);
-      for (int j = 0; j < num_kv; ++j) {
-        if (j + 1 < num_kv) {  // S_{j+1} runs on the tensor core while the softmax threads work on S_j
-          const int st = (j + 1) % 3;
-          ptx::mbar_wait(&kv_full[st], ((j + 1) / 3) & 1, 14);
-          ptx::tc_fence_after();
-          const uint32_t sK = sKV + st * 16384;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_ss(tmem_base + ((j + 1) & 1) * 64, desc_k(sQ, k), desc_k(sK, k), idesc_s, k > 0);
-          ptx::umma_commit(&s_full[(j + 1) & 1]);
-        }
-        ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1, 15);
+      // two cursors over the same (item, tile) sequence: the S = Q K^T issue runs one tile ahead of the P V issue, across
+      // item boundaries, so the tensor core computes S of the next tile while the softmax threads work on this one
+      int s_k = 0, s_it = sched_item(0, nitems), s_j = 0, s_n = s_it >= 0 ? tiles_of(s_it) : 0, s_gt = 0;
+      int p_k = 0, p_it = s_it, p_j = 0, p_n = s_n, p_gt = 0;
+      auto issue_s = [&]() {
+        if (s_j == 0) ptx::mbar_wait(&q_full[s_k & 1], (s_k >> 1) & 1, 12);
+        ptx::mbar_wait(&kv_full[s_gt % kFwdRing], (s_gt / kFwdRing) & 1, 13);
         ptx::tc_fence_after();
-        const uint32_t sV = sKV + (j % 3) * 16384 + 8192;
-        const uint32_t tP = tmem_base + (j & 1) * 64;  // bf16 P (32 packed columns) written over the consumed S tile
+        const uint32_t sQi = sQ + (s_k & 1) * 16384, sK = sKV + (s_gt % kFwdRing) * 16384;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ts(tm_O, tP + 8 * k, desc_mn(sV, k), idesc_o, (j > 0 || k > 0));
-        ptx::umma_commit(&kv_empty[j % 3]);
-        ptx::umma_commit(&p_empty[j & 1]);
+        for (int k = 0; k < 4; ++k) ptx::umma_ss(tmem_base + (s_gt & 1) * 64, desc_k(sQi, k), desc_k(sK, k), idesc_s, k > 0);
+        ptx::umma_commit(&s_full[s_gt & 1]);
+        if (s_j == s_n - 1) ptx::umma_commit(&q_empty[s_k & 1]);  // last S of the item: its Q tile may be overwritten
+        ++s_j;
+        ++s_gt;
+        if (s_j == s_n) {
+          ++s_k;
+          s_it = sched_item(s_k, nitems);
+          s_j = 0;
+          s_n = s_it >= 0 ? tiles_of(s_it) : 0;
+        }
+      };
+      if (s_it >= 0) issue_s();
+      while (p_it >= 0) {
+        if (s_it >= 0) issue_s();
+        if (p_j == 0 && p_k >= 2) ptx::mbar_wait(&o_free[p_k & 1], ((p_k >> 1) - 1) & 1, 14);  // item p_k-2 has been drained
+        ptx::mbar_wait(&p_full[p_gt & 1], (p_gt >> 1) & 1, 15);
+        ptx::tc_fence_after();
+        const uint32_t sV = sKV + (p_gt % kFwdRing) * 16384 + 8192;
+        const uint32_t tP = tmem_base + (p_gt & 1) * 64;  // bf16 P (32 packed columns) written over the consumed S tile
+        const uint32_t tO = tmem_base + 128 + (p_k & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_ts(tO, tP + 8 * k, desc_mn(sV, k), idesc_o, (p_j > 0 || k > 0));
+        ptx::umma_commit(&kv_empty[p_gt % kFwdRing]);
+        ptx::umma_commit(&p_empty[p_gt & 1]);
+        if (p_j == p_n - 1) ptx::umma_commit(&o_full[p_k & 1]);
+        ++p_j;
+        ++p_gt;
+        if (p_j == p_n) {
+          ++p_k;
+          p_it = sched_item(p_k, nitems);
+          p_j = 0;
+          p_n = p_it >= 0 ? tiles_of(p_it) : 0;
+        }
       }
-      ptx::umma_commit(o_full);
     }
     __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int r0 = qt * 128 + quarter * 32;  // first query row of this warp (relative to the sequence)
-    float m_ref = 0.f, l = 0.f;
-    const uint32_t drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(blockIdx.y * T + qt * 128 + r));
-    for (int j = 0; j < num_kv; ++j) {
-      const int bsel = j & 1;
-      const uint32_t tm_s = tmem_base + lane_off + bsel * 64;
-      // chunk classes of this warp for key columns [64j, 64j+32) and [64j+32, 64j+64)
-      const int c0 = j * 64, c1 = j * 64 + 32;
-      const int cls0 = (c0 + 31 <= r0) ? kFull : ((c0 > r0 + 31) ? kMasked : kDiag);
-      const int cls1 = (c1 + 31 <= r0) ? kFull : ((c1 > r0 + 31) ? kMasked : kDiag);
-      ATTN_STAMP(0);
-      ptx::mbar_wait(&s_full[bsel], (j >> 1) & 1, 17);
+    // item epilogue: O / l -> bf16, LSE.  The O buffer is released as soon as it sits in registers.  It runs AFTER the
+    // first tile of the following item: by then the last P V of this item has completed (no stall on o_full) and the
+    // tensor core already has the next S tiles to chew on.
+    auto epilogue = [&](int k, int it, float l, float m_ref) {
+      const int qt = nqt - 1 - it / BH, bh = it % BH, b = bh / H, h = bh % H;
+      const uint32_t tm_O = tmem_base + 128 + (k & 1) * 64;
+      ptx::mbar_wait(&o_full[k & 1], (k >> 1) & 1, 20);
       ptx::tc_fence_after();
-      ATTN_STAMP(1);
-      uint32_t pk[32];
-      float tmax = -1e30f, rowsum = 0.f;
-      if (j == 0) {
-        // first tile: the reference exponent is its true row max (cheap max-only pass, then the exp pass)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int cls = c == 0 ? cls0 : cls1;
-          if (cls == kFull) tmax = fmaxf(tmax, fwd_chunk_max<kFull>(tm_s + c * 32, lane));
-          else if (cls == kDiag) tmax = fmaxf(tmax, fwd_chunk_max<kDiag>(tm_s + c * 32, lane));
-        }
-        m_ref = tmax * kSl2;
-        fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
-      } else {
-        fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
-        const bool need = tmax * kSl2 - m_ref > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          // rare: raise the reference, rescale the O accumulator in TMEM, recompute this tile's P
-          const float m_new = need ? tmax * kSl2 : m_ref;
-          const float alpha = ex2(m_ref - m_new);
-          ptx::mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1, 19);  // every earlier P V product has landed in O
-          ptx::tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld32(tm_O + lane_off + c * 32, o);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            ptx::tmem_st32(tm_O + lane_off + c * 32, o);
-          }
-          ptx::tmem_st_wait();
-          l *= alpha;
-          m_ref = m_new;
-          tmax = -1e30f;
-          rowsum = 0.f;
-          fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
-        }
-      }
-      l += rowsum;
-      ATTN_STAMP(2);
-      ATTN_STAMP(3);
-      // P (64 key columns = 32 packed words) overwrites the first half of this tile's S buffer; the tensor pipe runs in
-      // issue order, so S_{j+2} cannot overwrite it before P V of this tile has consumed it
-      ptx::tmem_st16(tm_s, pk);
-      ptx::tmem_st16(tm_s + 16, pk + 16);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&p_full[bsel]);
-      ATTN_STAMP(4);
-    }
-#undef ATTN_STAMP
-    ptx::mbar_wait(o_full, 0, 20);
-    ptx::tc_fence_after();
-    const int t = qt * 128 + r;
-    const float inv = 1.0f / l;
-    __nv_bfloat16* o = out + static_cast<long long>(b * T + t) * C + h * HS;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tm_O + lane_off + c * 32, v);
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld32(tm_O + lane_off, v0);
+      ptx::tmem_ld32(tm_O + lane_off + 32, v1);
       ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&o_free[k & 1]);
+      const int t = qt * 128 + r;
       if (t < T) {
+        const float inv = 1.0f / l;
+        __nv_bfloat16* o = out + static_cast<long long>(b * T + t) * C + h * HS;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 w;
-          w.x = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
-          w.y = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
-          w.z = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
-          w.w = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
-          reinterpret_cast<uint4*>(o)[c * 4 + q] = w;
+          w.x = ptx::pack_bf16x2(__uint_as_float(v0[8 * q + 0]) * inv, __uint_as_float(v0[8 * q + 1]) * inv);
+          w.y = ptx::pack_bf16x2(__uint_as_float(v0[8 * q + 2]) * inv, __uint_as_float(v0[8 * q + 3]) * inv);
+          w.z = ptx::pack_bf16x2(__uint_as_float(v0[8 * q + 4]) * inv, __uint_as_float(v0[8 * q + 5]) * inv);
+          w.w = ptx::pack_bf16x2(__uint_as_float(v0[8 * q + 6]) * inv, __uint_as_float(v0[8 * q + 7]) * inv);
+          reinterpret_cast<uint4*>(o)[q] = w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = ptx::pack_bf16x2(__uint_as_float(v1[8 * q + 0]) * inv, __uint_as_float(v1[8 * q + 1]) * inv);
+          w.y = ptx::pack_bf16x2(__uint_as_float(v1[8 * q + 2]) * inv, __uint_as_float(v1[8 * q + 3]) * inv);
+          w.z = ptx::pack_bf16x2(__uint_as_float(v1[8 * q + 4]) * inv, __uint_as_float(v1[8 * q + 5]) * inv);
+          w.w = ptx::pack_bf16x2(__uint_as_float(v1[8 * q + 6]) * inv, __uint_as_float(v1[8 * q + 7]) * inv);
+          reinterpret_cast<uint4*>(o)[4 + q] = w;
+        }
+        lse[(static_cast<long long>(b) * H + h) * T + t] = (m_ref + log2f(l)) * kLn2;
+      }
+    };
+    bool pend = false;
+    int pend_k = 0, pend_it = 0;
+    float pend_l = 1.f, pend_m = 0.f;
+    int gt = 0;
+    for (int item_k = 0;; ++item_k) {
+      const int it = sched_item(item_k, nitems);
+      if (it < 0) break;
+      const int qt = nqt - 1 - it / BH, bh = it % BH;
+      const int num_kv = tiles_of(it);
+      total_steps += num_kv;
+      const uint32_t tm_O = tmem_base + 128 + (item_k & 1) * 64;
+      const int r0 = qt * 128 + quarter * 32;  // first query row of this warp (relative to the sequence)
+      float m_ref = 0.f, l = 0.f;
+      const uint32_t drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(bh * T + qt * 128 + r));
+      for (int j = 0; j < num_kv; ++j, ++gt) {
+        const int bsel = gt & 1;
+        const uint32_t tm_s = tmem_base + lane_off + bsel * 64;
+        // chunk classes of this warp for key columns [64j, 64j+32) and [64j+32, 64j+64)
+        const int c0 = j * 64, c1 = j * 64 + 32;
+        const int cls0 = (c0 + 31 <= r0) ? kFull : ((c0 > r0 + 31) ? kMasked : kDiag);
+        const int cls1 = (c1 + 31 <= r0) ? kFull : ((c1 > r0 + 31) ? kMasked : kDiag);
+        ATTN_STAMP(0);
+        ptx::mbar_wait(&s_full[bsel], (gt >> 1) & 1, 17);
+        ptx::tc_fence_after();
+        ATTN_STAMP(1);
+        uint32_t pk[32];
+        float tmax = -1e30f, rowsum = 0.f;
+        if (j == 0) {
+          // first tile: the reference exponent is its true row max (cheap max-only pass, then the exp pass)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int cls = c == 0 ? cls0 : cls1;
+            if (cls == kFull) tmax = fmaxf(tmax, fwd_chunk_max<kFull>(tm_s + c * 32, lane));
+            else if (cls == kDiag) tmax = fmaxf(tmax, fwd_chunk_max<kDiag>(tm_s + c * 32, lane));
+          }
+          m_ref = tmax * kSl2;
+          fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
+        } else {
+          fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
+          const bool need = tmax * kSl2 - m_ref > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            // rare: raise the reference, rescale the O accumulator in TMEM, recompute this tile's P
+            const float m_new = need ? tmax * kSl2 : m_ref;
+            const float alpha = ex2(m_ref - m_new);
+            ptx::mbar_wait(&p_empty[(gt - 1) & 1], ((gt - 1) >> 1) & 1, 19);  // every earlier P V product has landed in O
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[32];
+              ptx::tmem_ld32(tm_O + lane_off + c * 32, o);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              ptx::tmem_st32(tm_O + lane_off + c * 32, o);
+            }
+            ptx::tmem_st_wait();
+            l *= alpha;
+            m_ref = m_new;
+            tmax = -1e30f;
+            rowsum = 0.f;
+            fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
+          }
+        }
+        l += rowsum;
+        ATTN_STAMP(2);
+        ATTN_STAMP(3);
+        // P (64 key columns = 32 packed words) overwrites the first half of this tile's S buffer; the tensor pipe runs in
+        // issue order, so S_{j+2} cannot overwrite it before P V of this tile has consumed it
+        ptx::tmem_st16(tm_s, pk);
+        ptx::tmem_st16(tm_s + 16, pk + 16);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&p_full[bsel]);
+        ATTN_STAMP(4);
+        if (pend) {
+          epilogue(pend_k, pend_it, pend_l, pend_m);
+          pend = false;
         }
       }
+      // this item's epilogue is deferred until after the first tile of the next item (see below)
+      pend = true;
+      pend_k = item_k;
+      pend_it = it;
+      pend_l = l;
+      pend_m = m_ref;
     }
-    if (t < T) lse[(static_cast<long long>(b) * H + h) * T + t] = (m_ref + log2f(l)) * kLn2;
+    if (pend) epilogue(pend_k, pend_it, pend_l, pend_m);
+#undef ATTN_STAMP
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+  if (threadIdx.x == 64) cta_trace_write(cta_trace, cta_t0, total_steps);
 }
 
 // ======================================================================================================
@@ -519,55 +627,60 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
 // ======================================================================================================
 // backward: dQ and dK/dV
 // ======================================================================================================
-// Both backward kernels run ONE CTA per SM with two compute groups of 128 threads.  The score tiles S and dP
-// (128 x 64 fp32 each) are double-buffered in TMEM and buffer g belongs to group g: while group 0 turns S/dP of step j
-// into dS, the tensor core already produces S/dP of step j+1 for group 1, and the accumulating MMAs (dQ, or dV and dK)
-// of finished steps interleave in between.  Without this, every step serialises "MMA -> exp/dS -> MMA" (measured:
-// ~1400 of ~2700 cycles per step spent waiting for the score MMAs).
+// Both backward kernels run ONE persistent CTA per SM with two compute groups of 128 threads.  The score tiles S and dP
+// (128 x 64 fp32 each) are triple-buffered in TMEM and consecutive steps alternate between the groups: while group 0
+// turns S/dP of step j into dS, the tensor core already produces S/dP of step j+1 for group 1, and the accumulating
+// MMAs (dQ, or dV and dK) of finished steps interleave in between.  Step counters run freely across items, so the
+// producer and the score MMAs are already working on the next item while this item's accumulators are drained.
 constexpr int kSBuf = 3;          // S/dP score buffers in TMEM: two are being consumed by the two groups, one is being produced
 constexpr int kRing = 6;          // K/V (dQ kernel) or Q/dO (dK/dV kernel) tiles in flight: TMA latency >> one step
 constexpr int kBwdThreads = 352;  // warp 0 TMA, warp 1 score MMAs, warps 2..5 group 0, warps 6..9 group 1, warp 10 accumulating MMAs
 
 struct DqSmem {
-  static constexpr int Q = 0;         // 128 x 64
-  static constexpr int DO = 16384;    // 128 x 64
-  static constexpr int KV = 32768;    // kRing stages x (K 64x64 | V 64x64)
+  static constexpr int QDO = 0;       // 2 items x (Q 128x64 | dO 128x64)
+  static constexpr int KV = 65536;    // kRing stages x (K 64x64 | V 64x64)
   static constexpr int BAR = KV + kRing * 16384;  // dS never touches shared memory: it is written back into TMEM
-  static constexpr int TOTAL = BAR + 256 + 1024;
+  static constexpr int TOTAL = BAR + 512 + 1024;
 };
 
 template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                    const __grid_constant__ CUtensorMap tmDO128, const float* __restrict__ lse,
-                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, long long* trace,
-                   const DropCfg dcfg) {
-  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
-#define DQ_STAMP(k) do { if (tr) trace[j * 8 + (k)] = clock64(); } while (0)
+                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, int BH,
+                   int nitems, long long* trace, const DropCfg dcfg, long long* cta_trace) {
+  const long long cta_t0 = cta_trace ? globaltimer_ns() : 0;
+  const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+#define DQ_STAMP(k) do { if (tr && use < 64) trace[use * 8 + (k)] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DqSmem::BAR);
-  uint64_t* qdo_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                 // [kRing]
+  uint64_t* qdo_full = bars + 0;                // [2]
+  uint64_t* qdo_empty = bars + 2;               // [2]
+  uint64_t* kv_full = bars + 4;                 // [kRing]
   uint64_t* kv_empty = kv_full + kRing;         // [kRing]
   uint64_t* s_full = kv_empty + kRing;          // [kSBuf]
   uint64_t* s_free = s_full + kSBuf;            // [kSBuf] committed after the dQ MMA that read dS out of this buffer
-  uint64_t* ds_full = s_free + kSBuf;           // [2]
-  uint64_t* all_done = ds_full + 2;  // dedicated: a parity wait is only meaningful to a thread that followed every phase
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
+  uint64_t* ds_full = s_free + kSBuf;           // [kSBuf] one per score buffer (NOT per group: a group may finish two steps
+                                                //         while the dQ issuer waits for acc_free; a parity wait tolerates one phase)
+  uint64_t* acc_full = ds_full + kSBuf;         // [2] dQ accumulator of an item complete
+  uint64_t* acc_free = acc_full + 2;            // [2] ... and drained into registers by all 256 compute threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;
-  const int b = blockIdx.y / H, h = blockIdx.y % H;
-  const int row0 = b * T + qt * 128;
-  const int kv_end = min(T, qt * 128 + 128);
-  const int num_kv = (kv_end + 63) / 64;
+  const int nqt = (T + 127) / 128;
+  int total_steps = 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQKV128);
     ptx::prefetch_tmap(&tmQKV64);
     ptx::prefetch_tmap(&tmDO128);
-    ptx::mbar_init(qdo_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&qdo_full[s], 1);
+      ptx::mbar_init(&qdo_empty[s], 1);
+      ptx::mbar_init(&acc_full[s], 1);
+      ptx::mbar_init(&acc_free[s], 256);
+    }
     for (int s = 0; s < kRing; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
       ptx::mbar_init(&kv_empty[s], 1);
@@ -575,9 +688,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     for (int s = 0; s < kSBuf; ++s) {
       ptx::mbar_init(&s_full[s], 1);
       ptx::mbar_init(&s_free[s], 1);
+      ptx::mbar_init(&ds_full[s], 128);
     }
-    for (int s = 0; s < 2; ++s) ptx::mbar_init(&ds_full[s], 128);
-    ptx::mbar_init(all_done, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -588,63 +700,96 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_dQ = tmem_base + 128 * kSBuf;  // score buffer b: S at 128 b, dP at 128 b + 64
+  const uint32_t tm_dQ = tmem_base + 128 * kSBuf;  // score buffer b: S at 128 b, dP at 128 b + 64; dQ buffers at 384, 448
+
+  // number of 64-row K/V tiles of an item (item -> query tile nqt-1-rank: heaviest first)
+  auto tiles_of = [&](int it) {
+    const int qt = nqt - 1 - it / BH;
+    return (min(T, qt * 128 + 128) + 63) / 64;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(qdo_full, 32768);
-      ptx::tma_load_2d(smem + DqSmem::Q, &tmQKV128, qdo_full, h * HS, row0);
-      ptx::tma_load_2d(smem + DqSmem::DO, &tmDO128, qdo_full, h * HS, row0);
-      for (int j = 0; j < num_kv; ++j) {
-        const int st = j % kRing;
-        const uint32_t ph = (j / kRing) & 1;
-        ptx::mbar_wait(&kv_empty[st], ph ^ 1, 20);
-        ptx::mbar_expect_tx(&kv_full[st], 16384);
-        uint8_t* dst = smem + DqSmem::KV + st * 16384;
-        ptx::tma_load_2d(dst, &tmQKV64, &kv_full[st], C + h * HS, b * T + j * 64);
-        ptx::tma_load_2d(dst + 8192, &tmQKV64, &kv_full[st], 2 * C + h * HS, b * T + j * 64);
+      int gs = 0;
+      for (int k = 0;; ++k) {
+        const int it = sched_item(k, nitems);
+        if (it < 0) break;
+        const int qt = nqt - 1 - it / BH, bh = it % BH, b = bh / H, h = bh % H;
+        const int num_kv = tiles_of(it), row0 = b * T + qt * 128;
+        const int qb = k & 1;
+        ptx::mbar_wait(&qdo_empty[qb], ((k >> 1) & 1) ^ 1, 20);
+        ptx::mbar_expect_tx(&qdo_full[qb], 32768);
+        ptx::tma_load_2d(smem + DqSmem::QDO + qb * 32768, &tmQKV128, &qdo_full[qb], h * HS, row0);
+        ptx::tma_load_2d(smem + DqSmem::QDO + qb * 32768 + 16384, &tmDO128, &qdo_full[qb], h * HS, row0);
+        for (int j = 0; j < num_kv; ++j, ++gs) {
+          const int st = gs % kRing;
+          ptx::mbar_wait(&kv_empty[st], ((gs / kRing) & 1) ^ 1, 21);
+          ptx::mbar_expect_tx(&kv_full[st], 16384);
+          uint8_t* dst = smem + DqSmem::KV + st * 16384;
+          ptx::tma_load_2d(dst, &tmQKV64, &kv_full[st], C + h * HS, b * T + j * 64);
+          ptx::tma_load_2d(dst + 8192, &tmQKV64, &kv_full[st], 2 * C + h * HS, b * T + j * 64);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ---- score MMAs: S_j = Q K_j^T, dP_j = dO V_j^T into TMEM buffer j & 1 (one issuing thread per MMA family:
-    // a single thread issuing all twelve MMAs of a step plus its barrier traffic was the bottleneck)
+    // ---- score MMAs: S_j = Q K_j^T, dP_j = dO V_j^T into TMEM score buffer gs % kSBuf (one issuing thread per MMA
+    // family: a single thread issuing all twelve MMAs of a step plus its barrier traffic was the bottleneck)
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0, 0);
-      const uint64_t dQ0 = desc_k(ptx::smem_u32(smem + DqSmem::Q), 0), dDO0 = desc_k(ptx::smem_u32(smem + DqSmem::DO), 0);
+      const uint64_t dQDO0 = desc_k(ptx::smem_u32(smem + DqSmem::QDO), 0);
       const uint64_t dKV0 = desc_k(ptx::smem_u32(smem + DqSmem::KV), 0);
-      ptx::mbar_wait(qdo_full, 0, 21);
-      for (int j = 0; j < num_kv; ++j) {
-        ptx::mbar_wait(&kv_full[j % kRing], (j / kRing) & 1, 22);
-        if (j >= kSBuf) ptx::mbar_wait(&s_free[j % kSBuf], ((j / kSBuf) - 1) & 1, 23);  // the dQ MMA of step j-3 has read its dS
-        ptx::tc_fence_after();
-        const uint64_t dK = dKV0 + static_cast<uint64_t>((j % kRing) * (16384 >> 4)), dV = dK + (8192 >> 4);
-        const uint32_t tS = tmem_base + (j % kSBuf) * 128;
+      int gs = 0;
+      for (int k = 0;; ++k) {
+        const int it = sched_item(k, nitems);
+        if (it < 0) break;
+        const int num_kv = tiles_of(it);
+        const uint64_t dQ0 = dQDO0 + static_cast<uint64_t>((k & 1) * (32768 >> 4)), dDO0 = dQ0 + (16384 >> 4);
+        ptx::mbar_wait(&qdo_full[k & 1], (k >> 1) & 1, 22);
+        for (int j = 0; j < num_kv; ++j, ++gs) {
+          ptx::mbar_wait(&kv_full[gs % kRing], (gs / kRing) & 1, 23);
+          if (gs >= kSBuf) ptx::mbar_wait(&s_free[gs % kSBuf], ((gs / kSBuf) - 1) & 1, 24);  // the dQ MMA of step gs-3 has read its dS
+          ptx::tc_fence_after();
+          const uint64_t dK = dKV0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4)), dV = dK + (8192 >> 4);
+          const uint32_t tS = tmem_base + (gs % kSBuf) * 128;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tS, dQ0 + 2 * k, dK + 2 * k, idesc_s, k > 0);
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_ss(tS, dQ0 + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tS + 64, dDO0 + 2 * k, dV + 2 * k, idesc_s, k > 0);
-        ptx::umma_commit(&s_full[j % kSBuf]);
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_ss(tS + 64, dDO0 + 2 * kk, dV + 2 * kk, idesc_s, kk > 0);
+          ptx::umma_commit(&s_full[gs % kSBuf]);
+        }
+        ptx::umma_commit(&qdo_empty[k & 1]);  // all score MMAs of the item done: its Q / dO tiles may be overwritten
       }
     }
     __syncwarp();
   } else if (warp == 10) {
-    // ---- accumulating MMAs: dQ += dS_j K_j
+    // ---- accumulating MMAs: dQ += dS_j K_j  (dQ accumulator double-buffered by item parity)
     if (lane == 0) {
       constexpr uint32_t idesc_dq = ptx::umma_idesc_bf16(128, 64, 0, 1);
       const uint64_t dKmn0 = desc_mn(ptx::smem_u32(smem + DqSmem::KV), 0);
-      for (int j = 0; j < num_kv; ++j) {
-        ptx::mbar_wait(&ds_full[j & 1], (j >> 1) & 1, 23);
-        ptx::tc_fence_after();
-        // A = dS (bf16 pairs, 32 columns) sits in the first columns of this step's score buffer
-        const uint32_t tA = tmem_base + (j % kSBuf) * 128;
-        const uint64_t dK = dKmn0 + static_cast<uint64_t>((j % kRing) * (16384 >> 4));
+      int gs = 0;
+      for (int k = 0;; ++k) {
+        const int it = sched_item(k, nitems);
+        if (it < 0) break;
+        const int num_kv = tiles_of(it);
+        const uint32_t tAcc = tm_dQ + (k & 1) * 64;
+        if (k >= 2) {
+          ptx::mbar_wait(&acc_free[k & 1], ((k >> 1) - 1) & 1, 25);
+          ptx::tc_fence_after();
+        }
+        for (int j = 0; j < num_kv; ++j, ++gs) {
+          ptx::mbar_wait(&ds_full[gs % kSBuf], (gs / kSBuf) & 1, 26);
+          ptx::tc_fence_after();
+          // A = dS (bf16 pairs, 32 columns) sits in the first columns of this step's score buffer
+          const uint32_t tA = tmem_base + (gs % kSBuf) * 128;
+          const uint64_t dK = dKmn0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ts(tm_dQ, tA + 8 * k, dK + (2048 >> 4) * k, idesc_dq, (j > 0 || k > 0));
-        ptx::umma_commit(&kv_empty[j % kRing]);  // S_j / dP_j (other issuer) completed before ds_full(j) could complete
-        ptx::umma_commit(&s_free[j % kSBuf]);    // the score buffer (now holding dS) may be overwritten
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_ts(tAcc, tA + 8 * kk, dK + (2048 >> 4) * kk, idesc_dq, (j > 0 || kk > 0));
+          ptx::umma_commit(&kv_empty[gs % kRing]);  // S_j / dP_j (other issuer) completed before ds_full could complete
+          ptx::umma_commit(&s_free[gs % kSBuf]);    // the score buffer (now holding dS) may be overwritten
+        }
+        ptx::umma_commit(&acc_full[k & 1]);
       }
-      ptx::umma_commit(all_done);
     }
     __syncwarp();
   } else {
@@ -652,105 +797,167 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int t = qt * 128 + r;
-    const bool valid = t < T;
-    const long long stat_idx = (static_cast<long long>(b) * H + h) * T + t;
-    const float neg_lse2 = valid ? -__ldg(lse + stat_idx) * kLog2e : 0.f;
-    const float neg_delta8 = valid ? -__ldg(delta + stat_idx) * kScale : 0.f;
-    const int r0 = qt * 128 + quarter * 32;
-    const uint32_t drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(blockIdx.y * T + t));
-    for (int j = g; j < num_kv; j += 2) {
-      const int use = j >> 1;
-      DQ_STAMP(0);
-      ptx::mbar_wait(&s_full[j % kSBuf], (j / kSBuf) & 1, 24);
+    // per-item row statistics of this thread's query row: RAW values prefetched one item ahead (the scaling happens at
+    // the point of use, otherwise the multiply sits right behind the load and the warp eats the global-load latency)
+    auto load_stats = [&](int k, float& raw_l, float& raw_d) {
+      raw_l = 0.f;
+      raw_d = 0.f;
+      const int it = sched_item(k, nitems);
+      if (it < 0) return;
+      const int t = (nqt - 1 - it / BH) * 128 + r;
+      if (t < T) {
+        const long long idx = static_cast<long long>(it % BH) * T + t;
+        raw_l = __ldg(lse + idx);
+        raw_d = __ldg(delta + idx);
+      }
+    };
+    // item epilogue: group g writes columns [32 g, 32 g + 32) of dQ; the accumulator is released once it is in registers
+    auto epilogue = [&](int k) {
+      const int it = sched_item(k, nitems);
+      const int qt = nqt - 1 - it / BH, bh = it % BH, b = bh / H, h = bh % H;
+      const int t = qt * 128 + r;
+      ptx::mbar_wait(&acc_full[k & 1], (k >> 1) & 1, 27);
       ptx::tc_fence_after();
+      uint32_t v[32];
+      ptx::tmem_ld32(tm_dQ + (k & 1) * 64 + lane_off + g * 32, v);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&acc_free[k & 1]);
+      if (t < T) {
+        __nv_bfloat16* o = dqkv + static_cast<long long>(b * T + t) * (3 * C) + h * HS + g * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+          w.y = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+          w.z = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+          w.w = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+          reinterpret_cast<uint4*>(o)[q] = w;
+        }
+      }
+    };
+    // cursor over this group's steps: item pass c_k, step c_n inside the item, global step c_base + c_n (parity == g)
+    int c_k = 0, c_it = sched_item(0, nitems), c_n = g, c_base = 0, c_nq = c_it >= 0 ? tiles_of(c_it) : 0;
+    auto normalize = [&]() {
+      while (c_it >= 0 && c_n >= c_nq) {
+        c_n -= c_nq;
+        c_base += c_nq;
+        ++c_k;
+        c_it = sched_item(c_k, nitems);
+        c_nq = c_it >= 0 ? tiles_of(c_it) : 0;
+      }
+    };
+    normalize();
+    int ep_k = 0, stat_k = -1, nxt_k = c_k, use = 0;
+    int r0 = 0;
+    uint32_t drop_rk = 0;
+    float neg_l = 0.f, neg_d = 0.f, nxt_l, nxt_d;
+    load_stats(c_k, nxt_l, nxt_d);
+    while (c_it >= 0) {
+      DQ_STAMP(0);
+      if (stat_k != c_k) {  // first own step in a new item: decode it once, take its row statistics, prefetch the next item's
+        if (nxt_k != c_k) load_stats(c_k, nxt_l, nxt_d);  // (prefetch guessed another item: never at the shapes in use)
+        neg_l = -nxt_l * kLog2e;
+        neg_d = -nxt_d * kScale;
+        const int qt = nqt - 1 - c_it / BH, bh = c_it % BH;
+        r0 = qt * 128 + quarter * 32;
+        if (DROP) drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(bh * T + qt * 128 + r));
+        stat_k = c_k;
+        // the next item this group touches is c_k + 1 unless that item has a single step owned by the other group
+        int nk = c_k + 1;
+        {
+          const int nit = sched_item(nk, nitems);
+          if (nit >= 0 && tiles_of(nit) == 1 && ((c_base + c_nq) & 1) != g) ++nk;
+        }
+        load_stats(nk, nxt_l, nxt_d);
+        nxt_k = nk;
+      }
+      const int gs = c_base + c_n;
       DQ_STAMP(1);
-      const uint32_t tbuf = tmem_base + lane_off + (j % kSBuf) * 128;
+      ptx::mbar_wait(&s_full[gs % kSBuf], (gs / kSBuf) & 1, 28);
+      ptx::tc_fence_after();
+      DQ_STAMP(2);
+      const uint32_t tbuf = tmem_base + lane_off + (gs % kSBuf) * 128;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const int c0 = j * 64 + c * 32;
+        const int c0 = c_n * 64 + c * 32;
         const uint32_t ta_s = tbuf + c * 32, ta_dp = ta_s + 64;
         uint32_t pk[16];
-        if (c0 + 31 <= r0) dq_chunk<kFull, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk, dcfg, drop_rk, c0);
-        else if (c0 > r0 + 31) dq_chunk<kMasked, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk, dcfg, drop_rk, c0);
-        else dq_chunk<kDiag, DROP>(ta_s, ta_dp, lane, neg_lse2, neg_delta8, pk, dcfg, drop_rk, c0);
+        if (c0 + 31 <= r0) dq_chunk<kFull, DROP>(ta_s, ta_dp, lane, neg_l, neg_d, pk, dcfg, drop_rk, c0);
+        else if (c0 > r0 + 31) dq_chunk<kMasked, DROP>(ta_s, ta_dp, lane, neg_l, neg_d, pk, dcfg, drop_rk, c0);
+        else dq_chunk<kDiag, DROP>(ta_s, ta_dp, lane, neg_l, neg_d, pk, dcfg, drop_rk, c0);
         // dS chunk c (32 key columns = 16 packed words) overwrites score columns that this thread has already consumed
         ptx::tmem_st16(tbuf + c * 16, pk);
       }
-      DQ_STAMP(2);
       DQ_STAMP(3);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&ds_full[g]);
+      ptx::mbar_arrive(&ds_full[gs % kSBuf]);
       DQ_STAMP(4);
+      if (tr && use < 64) { trace[use * 8 + 5] = c_k; trace[use * 8 + 6] = c_n; }
+      ++use;
+      ++total_steps;
+      // earlier items are drained AFTER this group's first step in a later item: by then their last MMAs (which wait for
+      // the other group's final step) have completed, so the drain does not stall the step pipeline
+      while (ep_k < c_k) epilogue(ep_k++);
+      c_n += 2;
+      normalize();
     }
 #undef DQ_STAMP
-    ptx::mbar_wait(all_done, 0, 26);  // committed after the last MMA
-    ptx::tc_fence_after();
-    // group g writes columns [32 g, 32 g + 32) of dQ
-    __nv_bfloat16* o = dqkv + static_cast<long long>(b * T + t) * (3 * C) + h * HS + g * 32;
-    uint32_t v[32];
-    ptx::tmem_ld32(tm_dQ + lane_off + g * 32, v);
-    ptx::tmem_ld_wait();
-    if (valid) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 w;
-        w.x = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-        w.y = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-        w.z = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-        w.w = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-        reinterpret_cast<uint4*>(o)[q] = w;
-      }
-    }
+    // items not yet drained (c_k is now one past the last item of this CTA)
+    while (ep_k < c_k) epilogue(ep_k++);
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 64) cta_trace_write(cta_trace, cta_t0, 2 * total_steps);
 }
 
 struct DkvSmem {
-  static constexpr int K = 0;          // 128 x 64
-  static constexpr int V = 16384;      // 128 x 64
-  static constexpr int QDO = 32768;    // kRing stages x (Q 64x64 | dO 64x64)
+  static constexpr int KV = 0;         // 2 items x (K 128x64 | V 128x64)
+  static constexpr int QDO = 65536;    // kRing stages x (Q 64x64 | dO 64x64)
   // P^T and dS^T never touch shared memory: they are written back into TMEM and consumed as the A operand from there
   static constexpr int STAT = QDO + kRing * 16384;  // 2 groups x 2 buffers x (-lse2[64] | -delta8[64] | dropout row key[64])
   static constexpr int BAR = STAT + 3072;
-  static constexpr int TOTAL = BAR + 256 + 1024;
+  static constexpr int TOTAL = BAR + 512 + 1024;
 };
 
 template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                     const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
-                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, long long* trace,
-                    const DropCfg dcfg) {
-  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
-#define DKV_STAMP(k) do { if (tr) trace[128 + n * 8 + (k)] = clock64(); } while (0)
+                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, int BH,
+                    int nitems, long long* trace, const DropCfg dcfg, long long* cta_trace) {
+  const long long cta_t0 = cta_trace ? globaltimer_ns() : 0;
+  const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+#define DKV_STAMP(k) do { if (tr && use < 64) trace[512 + use * 8 + (k)] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DkvSmem::BAR);
-  uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;                // [kRing]
+  uint64_t* kv_full = bars + 0;                 // [2]
+  uint64_t* kv_empty = bars + 2;                // [2]
+  uint64_t* qdo_full = bars + 4;                // [kRing]
   uint64_t* qdo_empty = qdo_full + kRing;       // [kRing]
   uint64_t* s_full = qdo_empty + kRing;         // [kSBuf]
   uint64_t* s_free = s_full + kSBuf;            // [kSBuf] committed after the dV / dK MMAs that read P^T / dS^T out of the buffer
-  uint64_t* pds_full = s_free + kSBuf;          // [2]
-  uint64_t* all_done = pds_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
+  uint64_t* pds_full = s_free + kSBuf;          // [kSBuf] one per score buffer (see the dQ kernel)
+  uint64_t* acc_full = pds_full + kSBuf;        // dV / dK accumulators of an item complete
+  uint64_t* acc_free = acc_full + 1;            // ... and drained into registers by all 256 compute threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
   float* stat = reinterpret_cast<float*>(smem + DkvSmem::STAT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x;  // key tile; tile 0 is the heaviest and is scheduled first
-  const int b = blockIdx.y / H, h = blockIdx.y % H;
-  const int i0 = kt * 2;                // first 64-row query tile that can see this key tile
-  const int nq = (T + 63) / 64 - i0;    // >= 1
+  const int nq64 = (T + 63) / 64;
+  int total_steps = 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQKV128);
     ptx::prefetch_tmap(&tmQKV64);
     ptx::prefetch_tmap(&tmDO64);
-    ptx::mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+    }
     for (int s = 0; s < kRing; ++s) {
       ptx::mbar_init(&qdo_full[s], 1);
       ptx::mbar_init(&qdo_empty[s], 1);
@@ -758,9 +965,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     for (int s = 0; s < kSBuf; ++s) {
       ptx::mbar_init(&s_full[s], 1);
       ptx::mbar_init(&s_free[s], 1);
+      ptx::mbar_init(&pds_full[s], 128);
     }
-    for (int s = 0; s < 2; ++s) ptx::mbar_init(&pds_full[s], 128);
-    ptx::mbar_init(all_done, 1);
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_free, 256);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -773,40 +981,59 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_dV = tmem_base + 128 * kSBuf, tm_dK = tm_dV + 64;  // score buffer b: S^T at 128 b, dP^T at 128 b + 64
 
+  // item -> key tile kt = rank (tile 0 sees every query tile: heaviest first); steps = 64-row query tiles from 2 kt on
+  auto steps_of = [&](int it) { return nq64 - (it / BH) * 2; };
+
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(kv_full, 32768);
-      ptx::tma_load_2d(smem + DkvSmem::K, &tmQKV128, kv_full, C + h * HS, b * T + kt * 128);
-      ptx::tma_load_2d(smem + DkvSmem::V, &tmQKV128, kv_full, 2 * C + h * HS, b * T + kt * 128);
-      for (int n = 0; n < nq; ++n) {
-        const int st = n % kRing;
-        const uint32_t ph = (n / kRing) & 1;
-        ptx::mbar_wait(&qdo_empty[st], ph ^ 1, 30);
-        ptx::mbar_expect_tx(&qdo_full[st], 16384);
-        uint8_t* dst = smem + DkvSmem::QDO + st * 16384;
-        ptx::tma_load_2d(dst, &tmQKV64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
-        ptx::tma_load_2d(dst + 8192, &tmDO64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
+      int gs = 0;
+      for (int k = 0;; ++k) {
+        const int it = sched_item(k, nitems);
+        if (it < 0) break;
+        const int kt = it / BH, bh = it % BH, b = bh / H, h = bh % H;
+        const int i0 = kt * 2, nq = steps_of(it);
+        const int kb = k & 1;
+        ptx::mbar_wait(&kv_empty[kb], ((k >> 1) & 1) ^ 1, 30);
+        ptx::mbar_expect_tx(&kv_full[kb], 32768);
+        ptx::tma_load_2d(smem + DkvSmem::KV + kb * 32768, &tmQKV128, &kv_full[kb], C + h * HS, b * T + kt * 128);
+        ptx::tma_load_2d(smem + DkvSmem::KV + kb * 32768 + 16384, &tmQKV128, &kv_full[kb], 2 * C + h * HS, b * T + kt * 128);
+        for (int n = 0; n < nq; ++n, ++gs) {
+          const int st = gs % kRing;
+          ptx::mbar_wait(&qdo_empty[st], ((gs / kRing) & 1) ^ 1, 31);
+          ptx::mbar_expect_tx(&qdo_full[st], 16384);
+          uint8_t* dst = smem + DkvSmem::QDO + st * 16384;
+          ptx::tma_load_2d(dst, &tmQKV64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
+          ptx::tma_load_2d(dst + 8192, &tmDO64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ---- score MMAs: S^T_n = K Q_n^T, dP^T_n = V dO_n^T into TMEM buffer n & 1
+    // ---- score MMAs: S^T_n = K Q_n^T, dP^T_n = V dO_n^T into TMEM score buffer gs % kSBuf
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0, 0);
-      const uint64_t dK0 = desc_k(ptx::smem_u32(smem + DkvSmem::K), 0), dV0 = desc_k(ptx::smem_u32(smem + DkvSmem::V), 0);
+      const uint64_t dKV0 = desc_k(ptx::smem_u32(smem + DkvSmem::KV), 0);
       const uint64_t dQDO0 = desc_k(ptx::smem_u32(smem + DkvSmem::QDO), 0);
-      ptx::mbar_wait(kv_full, 0, 31);
-      for (int n = 0; n < nq; ++n) {
-        ptx::mbar_wait(&qdo_full[n % kRing], (n / kRing) & 1, 32);
-        if (n >= kSBuf) ptx::mbar_wait(&s_free[n % kSBuf], ((n / kSBuf) - 1) & 1, 33);  // dV / dK of step n-3 have read it
-        ptx::tc_fence_after();
-        const uint64_t dQ = dQDO0 + static_cast<uint64_t>((n % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
-        const uint32_t tS = tmem_base + (n % kSBuf) * 128;
+      int gs = 0;
+      for (int k = 0;; ++k) {
+        const int it = sched_item(k, nitems);
+        if (it < 0) break;
+        const int nq = steps_of(it);
+        const uint64_t dK0 = dKV0 + static_cast<uint64_t>((k & 1) * (32768 >> 4)), dV0 = dK0 + (16384 >> 4);
+        ptx::mbar_wait(&kv_full[k & 1], (k >> 1) & 1, 32);
+        for (int n = 0; n < nq; ++n, ++gs) {
+          ptx::mbar_wait(&qdo_full[gs % kRing], (gs / kRing) & 1, 33);
+          if (gs >= kSBuf) ptx::mbar_wait(&s_free[gs % kSBuf], ((gs / kSBuf) - 1) & 1, 34);  // dV / dK of step gs-3 have read it
+          ptx::tc_fence_after();
+          const uint64_t dQ = dQDO0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
+          const uint32_t tS = tmem_base + (gs % kSBuf) * 128;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tS, dK0 + 2 * k, dQ + 2 * k, idesc_s, k > 0);
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_ss(tS, dK0 + 2 * kk, dQ + 2 * kk, idesc_s, kk > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tS + 64, dV0 + 2 * k, dDO + 2 * k, idesc_s, k > 0);
-        ptx::umma_commit(&s_full[n % kSBuf]);
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_ss(tS + 64, dV0 + 2 * kk, dDO + 2 * kk, idesc_s, kk > 0);
+          ptx::umma_commit(&s_full[gs % kSBuf]);
+        }
+        ptx::umma_commit(&kv_empty[k & 1]);  // all score MMAs of the item done: its K / V tiles may be overwritten
       }
     }
     __syncwarp();
@@ -815,19 +1042,29 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc_g = ptx::umma_idesc_bf16(128, 64, 0, 1);
       const uint64_t dQmn0 = desc_mn(ptx::smem_u32(smem + DkvSmem::QDO), 0);
-      for (int n = 0; n < nq; ++n) {
-        ptx::mbar_wait(&pds_full[n & 1], (n >> 1) & 1, 33);
-        ptx::tc_fence_after();
-        const uint32_t tP = tmem_base + (n % kSBuf) * 128, tDS = tP + 64;  // bf16 pairs written over the consumed scores
-        const uint64_t dQ = dQmn0 + static_cast<uint64_t>((n % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
+      int gs = 0;
+      for (int k = 0;; ++k) {
+        const int it = sched_item(k, nitems);
+        if (it < 0) break;
+        const int nq = steps_of(it);
+        if (k >= 1) {  // the previous item's dV / dK have been read out of TMEM
+          ptx::mbar_wait(acc_free, (k - 1) & 1, 35);
+          ptx::tc_fence_after();
+        }
+        for (int n = 0; n < nq; ++n, ++gs) {
+          ptx::mbar_wait(&pds_full[gs % kSBuf], (gs / kSBuf) & 1, 36);
+          ptx::tc_fence_after();
+          const uint32_t tP = tmem_base + (gs % kSBuf) * 128, tDS = tP + 64;  // bf16 pairs written over the consumed scores
+          const uint64_t dQ = dQmn0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ts(tm_dV, tP + 8 * k, dDO + (2048 >> 4) * k, idesc_g, (n > 0 || k > 0));
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_ts(tm_dV, tP + 8 * kk, dDO + (2048 >> 4) * kk, idesc_g, (n > 0 || kk > 0));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ts(tm_dK, tDS + 8 * k, dQ + (2048 >> 4) * k, idesc_g, (n > 0 || k > 0));
-        ptx::umma_commit(&qdo_empty[n % kRing]);
-        ptx::umma_commit(&s_free[n % kSBuf]);
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_ts(tm_dK, tDS + 8 * kk, dQ + (2048 >> 4) * kk, idesc_g, (n > 0 || kk > 0));
+          ptx::umma_commit(&qdo_empty[gs % kRing]);
+          ptx::umma_commit(&s_free[gs % kSBuf]);
+        }
+        ptx::umma_commit(acc_full);
       }
-      ptx::umma_commit(all_done);
     }
     __syncwarp();
   } else {
@@ -836,28 +1073,94 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     const int r = quarter * 32 + lane;      // key row inside the tile
     const int tid = (warp - 2 - 4 * g) * 32 + lane;  // 0..127 within the group
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int kv_t = kt * 128 + r;
-    const bool valid = kv_t < T;
-    const long long stat_base = (static_cast<long long>(b) * H + h) * T;
-    const int r0 = kt * 128 + quarter * 32;
-    for (int n = g; n < nq; n += 2) {
-      const int use = n >> 1;
-      const int q0 = (i0 + n) * 64;
-      float* st_lse = stat + (g * 2 + (use & 1)) * 192;
-      {
-        const int qi = q0 + (tid & 63);
-        float v = 0.f;
-        if (qi < T) v = (tid < 64) ? -__ldg(lse + stat_base + qi) * kLog2e : -__ldg(delta + stat_base + qi) * kScale;
-        st_lse[tid] = v;
-        if (DROP && tid < 64)
-          st_lse[128 + tid] = __uint_as_float(drop_row_key(dcfg.key, static_cast<uint32_t>(blockIdx.y * T + qi)));
+    // per-step column statistics (lse for threads 0..63, delta for threads 64..127 of the group): the RAW value of the
+    // next own step is loaded one step ahead and scaled only when it is stored to shared memory, so the global-load
+    // latency hides behind a whole step of arithmetic
+    const float* stat_src = tid < 64 ? lse : delta;
+    const float stat_coef = tid < 64 ? -kLog2e : -kScale;
+    auto load_stat = [&](int it, int n) {
+      float v = 0.f;
+      if (it >= 0) {
+        const int qi = ((it / BH) * 2 + n) * 64 + (tid & 63);
+        if (qi < T) v = __ldg(stat_src + static_cast<long long>(it % BH) * T + qi);
       }
-      DKV_STAMP(0);
-      ptx::bar_sync(1 + g, 128);
-      ptx::mbar_wait(&s_full[n % kSBuf], (n / kSBuf) & 1, 34);
+      return v;
+    };
+    // item epilogue: group 0 writes dV, group 1 writes dK; the accumulators are released once they sit in registers
+    auto epilogue = [&](int k) {
+      const int it = sched_item(k, nitems);
+      const int kt = it / BH, bh = it % BH, b = bh / H, h = bh % H;
+      const int kv_t = kt * 128 + r;
+      ptx::mbar_wait(acc_full, k & 1, 37);
       ptx::tc_fence_after();
+      const uint32_t tm = (g == 0 ? tm_dV : tm_dK) + lane_off;
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld32(tm, v0);
+      ptx::tmem_ld32(tm + 32, v1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(acc_free);
+      if (kv_t < T) {
+        __nv_bfloat16* o = dqkv + static_cast<long long>(b * T + kv_t) * (3 * C) + (g == 0 ? 2 * C : C) + h * HS;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = ptx::pack_bf16x2(__uint_as_float(v0[8 * q + 0]), __uint_as_float(v0[8 * q + 1]));
+          w.y = ptx::pack_bf16x2(__uint_as_float(v0[8 * q + 2]), __uint_as_float(v0[8 * q + 3]));
+          w.z = ptx::pack_bf16x2(__uint_as_float(v0[8 * q + 4]), __uint_as_float(v0[8 * q + 5]));
+          w.w = ptx::pack_bf16x2(__uint_as_float(v0[8 * q + 6]), __uint_as_float(v0[8 * q + 7]));
+          reinterpret_cast<uint4*>(o)[q] = w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = ptx::pack_bf16x2(__uint_as_float(v1[8 * q + 0]), __uint_as_float(v1[8 * q + 1]));
+          w.y = ptx::pack_bf16x2(__uint_as_float(v1[8 * q + 2]), __uint_as_float(v1[8 * q + 3]));
+          w.z = ptx::pack_bf16x2(__uint_as_float(v1[8 * q + 4]), __uint_as_float(v1[8 * q + 5]));
+          w.w = ptx::pack_bf16x2(__uint_as_float(v1[8 * q + 6]), __uint_as_float(v1[8 * q + 7]));
+          reinterpret_cast<uint4*>(o)[4 + q] = w;
+        }
+      }
+    };
+    // cursor over this group's steps (global step parity == g) and a look-ahead cursor one own step further
+    int c_k = 0, c_it = sched_item(0, nitems), c_n = g, c_base = 0, c_nq = c_it >= 0 ? steps_of(c_it) : 0;
+    auto normalize = [&](int& k, int& it, int& n, int& base, int& nq) {
+      while (it >= 0 && n >= nq) {
+        n -= nq;
+        base += nq;
+        ++k;
+        it = sched_item(k, nitems);
+        nq = it >= 0 ? steps_of(it) : 0;
+      }
+    };
+    normalize(c_k, c_it, c_n, c_base, c_nq);
+    int a_k = c_k, a_it = c_it, a_n = c_n + 2, a_base = c_base, a_nq = c_nq;
+    normalize(a_k, a_it, a_n, a_base, a_nq);
+    float raw_cur = load_stat(c_it, c_n);
+    int ep_k = 0, use = 0, dec_k = -1;
+    int kt = 0, bh = 0;
+    while (c_it >= 0) {
+      DKV_STAMP(0);
+      if (dec_k != c_k) {  // decode the item once
+        kt = c_it / BH;
+        bh = c_it % BH;
+        dec_k = c_k;
+      }
+      const int kv_t = kt * 128 + r;
+      const int r0 = kt * 128 + quarter * 32;
+      const int q0 = (kt * 2 + c_n) * 64;
+      const int gs = c_base + c_n;
+      float* st_lse = stat + (g * 2 + (use & 1)) * 192;
+      st_lse[tid] = raw_cur * stat_coef;
+      if (DROP && tid < 64)
+        st_lse[128 + tid] = __uint_as_float(drop_row_key(dcfg.key, static_cast<uint32_t>(bh * T + q0 + tid)));
+      raw_cur = load_stat(a_it, a_n);  // next own step: consumed at the top of the next iteration
       DKV_STAMP(1);
-      const uint32_t tbuf = tmem_base + lane_off + (n % kSBuf) * 128;
+      ptx::bar_sync(1 + g, 128);
+      ptx::mbar_wait(&s_full[gs % kSBuf], (gs / kSBuf) & 1, 38);
+      ptx::tc_fence_after();
+      DKV_STAMP(2);
+      const uint32_t tbuf = tmem_base + lane_off + (gs % kSBuf) * 128;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int c0 = q0 + c * 32;
@@ -871,40 +1174,28 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         ptx::tmem_st16(tbuf + c * 16, pk_p);
         ptx::tmem_st16(tbuf + 64 + c * 16, pk_ds);
       }
-      DKV_STAMP(2);
       DKV_STAMP(3);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&pds_full[g]);
+      ptx::mbar_arrive(&pds_full[gs % kSBuf]);
       DKV_STAMP(4);
+      if (tr && use < 64) { trace[512 + use * 8 + 5] = c_k; trace[512 + use * 8 + 6] = c_n; }
+      ++use;
+      ++total_steps;
+      // earlier items are drained AFTER this group's first step in a later item (their last MMAs wait for the other
+      // group's final step; by now they have completed): the drain does not stall the step pipeline
+      while (ep_k < c_k) epilogue(ep_k++);
+      c_k = a_k; c_it = a_it; c_n = a_n; c_base = a_base; c_nq = a_nq;
+      a_n += 2;
+      normalize(a_k, a_it, a_n, a_base, a_nq);
     }
 #undef DKV_STAMP
-    ptx::mbar_wait(all_done, 0, 36);  // committed after the last MMA
-    ptx::tc_fence_after();
-    // group 0 writes dV, group 1 writes dK
-    __nv_bfloat16* o = dqkv + static_cast<long long>(b * T + kv_t) * (3 * C) + (g == 0 ? 2 * C : C) + h * HS;
-    const uint32_t tm = g == 0 ? tm_dV : tm_dK;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tm + lane_off + c * 32, v);
-      ptx::tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w;
-          w.x = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-          w.y = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-          w.z = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-          w.w = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-          reinterpret_cast<uint4*>(o)[c * 4 + q] = w;
-        }
-      }
-    }
+    while (ep_k < c_k) epilogue(ep_k++);  // c_k is now one past the last item of this CTA
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 64) cta_trace_write(cta_trace, cta_t0, 2 * total_steps);
 }
 
 template <typename K>
@@ -917,7 +1208,7 @@ int set_smem(K kern, int bytes) {
 
 int check_shape(const char* who, int B, int T, int H) {
   ABCGPT_CHECK_ARG(B > 0 && T > 0 && H > 0, "%s: bad shape B=%d T=%d H=%d", who, B, T, H);
-  ABCGPT_CHECK_ARG(static_cast<long long>(B) * H <= 65535, "%s: B*H must be <= 65535 (grid.y)", who);
+  ABCGPT_CHECK_ARG(static_cast<long long>(B) * H * ((T + 127) / 128) < (1ll << 30), "%s: too many (tile, batch*head) items", who);
   return 0;
 }
 
@@ -940,13 +1231,15 @@ int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float 
     if ((rc = set_smem(attn_fwd_kernel<true>, FwdSmem::TOTAL))) return rc;
     done = true;
   }
-  dim3 grid((T + 127) / 128, B * H);
+  const int BH = B * H, nitems = ((T + 127) / 128) * BH;
+  const int grid = nitems < 2 * sm_count() ? nitems : 2 * sm_count();  // persistent: two CTAs per SM
+  long long* CT = g_attn_cta_trace;
   if (dcfg.thr16 == 0)
     attn_fwd_kernel<false><<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
-                                                                       T, H, C, g_attn_trace, dcfg);
+                                                                       T, H, C, BH, nitems, g_attn_trace, dcfg, CT);
   else
     attn_fwd_kernel<true><<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
-                                                                      T, H, C, g_attn_trace, dcfg);
+                                                                      T, H, C, BH, nitems, g_attn_trace, dcfg, CT);
   return launch_status("attn_fwd_kernel");
 }
 
@@ -978,20 +1271,23 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
         reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T, H, C);
     if ((rc = launch_status("attn_delta_kernel"))) return rc;
   }
-  dim3 grid((T + 127) / 128, B * H);
+  const int BH = B * H, nitems = ((T + 127) / 128) * BH;
+  const int grid = nitems < sm_count() ? nitems : sm_count();  // persistent: one CTA per SM
   __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  long long* CT1 = g_attn_cta_trace ? g_attn_cta_trace + 4 * 1024 : nullptr;
+  long long* CT2 = g_attn_cta_trace ? g_attn_cta_trace + 8 * 1024 : nullptr;
   if (dcfg.thr16 == 0) {
     attn_bwd_dkv_kernel<false><<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
-                                                                              g_attn_trace, dcfg);
+                                                                              BH, nitems, g_attn_trace, dcfg, CT1);
     if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
     attn_bwd_dq_kernel<false><<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
-                                                                            g_attn_trace, dcfg);
+                                                                            BH, nitems, g_attn_trace, dcfg, CT2);
   } else {
     attn_bwd_dkv_kernel<true><<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
-                                                                             g_attn_trace, dcfg);
+                                                                             BH, nitems, g_attn_trace, dcfg, CT1);
     if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
     attn_bwd_dq_kernel<true><<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
-                                                                           g_attn_trace, dcfg);
+                                                                           BH, nitems, g_attn_trace, dcfg, CT2);
   }
   return launch_status("attn_bwd_dq_kernel");
 }

@@ -24,21 +24,25 @@ for j in range(n):
     print(j, (r[1] - r[0]).item(), (r[2] - r[1]).item(), (r[3] - r[2]).item(), (r[4] - r[3]).item(), "|", (r[4] - r[0]).item())
 print("whole CTA:", (t[n - 1][4] - t[0][0]).item(), "cycles")
 
-# backward kernels: dq stamps at [0,128), dkv at [128,256)
+# backward kernels: stamps of group 0's first 64 own steps (across items): dq at [0,512), dkv at [512,1024)
 do = torch.randn(B * T, C, device="cuda").bfloat16()
 dqkv = torch.empty(B * T, 3 * C, device="cuda", dtype=torch.bfloat16)
 delta = torch.empty(B, H, T, device="cuda")
 for _ in range(2):
     ops.attn_bwd(qkv, o, do, lse, delta, dqkv, B, T, H)
-tr2 = torch.zeros(256, device="cuda", dtype=torch.int64)
+tr2 = torch.zeros(1024, device="cuda", dtype=torch.int64)
 _C.lib().abcgpt_debug_attn_trace(tr2.data_ptr())
 ops.attn_bwd(qkv, o, do, lse, delta, dqkv, B, T, H)
 torch.cuda.synchronize()
 _C.lib().abcgpt_debug_attn_trace(0)
-for name, base in (("dq", 0), ("dkv", 128)):
-    t = tr2[base:base + 128].view(16, 8).cpu()
-    print(name, "step: wait_S  compute  wait_prev_mma  store+arrive | total")
-    for j in range(16):
+for name, base in (("dq", 0), ("dkv", 512)):
+    t = tr2[base:base + 512].view(64, 8).cpu()
+    print(name, "own step: item n | epilogues  wait_S  compute  store+arrive | total | since previous step start")
+    prev = None
+    for j in range(64):
         r = t[j]
-        print(j, (r[1] - r[0]).item(), (r[2] - r[1]).item(), (r[3] - r[2]).item(), (r[4] - r[3]).item(), "|", (r[4] - r[0]).item())
-    print(name, "whole:", (t[15][4] - t[0][0]).item())
+        if r[4] == 0:
+            break
+        print(j, int(r[5]), int(r[6]), "|", (r[1] - r[0]).item(), (r[2] - r[1]).item(), (r[3] - r[2]).item(), (r[4] - r[3]).item(), "|",
+              (r[4] - r[0]).item(), "|", (r[0] - prev).item() if prev is not None else 0)
+        prev = r[0]
