@@ -4,7 +4,7 @@
 #include "kernels.h"
 
 using namespace abcgpt;
-namespace abcgpt { extern unsigned long long* g_gemm_stats; extern long long* g_attn_trace; extern long long* g_attn_cta_trace; }
+namespace abcgpt { extern unsigned long long* g_gemm_stats; extern long long* g_attn_trace; extern long long* g_attn_cta_trace; int tmem_ld_bench(long long*, int, int, int, cudaStream_t); }
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
 
@@ -98,6 +98,11 @@ int abcgpt_debug_gemm_stats(void* device_counters) {
 int abcgpt_debug_attn_cta_trace(void* device_records) {
   abcgpt::g_attn_cta_trace = reinterpret_cast<long long*>(device_records);
   return 0;
+}
+
+/* debug: cycles of `iters` x (inflight x tcgen05.ld 32x32b.x32 + wait) on nwarps warps of one CTA; out[warp] */
+int abcgpt_debug_tmem_ld_bench(void* out, int iters, int nwarps, int inflight, void* stream) {
+  return abcgpt::tmem_ld_bench(reinterpret_cast<long long*>(out), iters, nwarps, inflight, S(stream));
 }
 
 int abcgpt_debug_attn_trace(void* device_stamps) {

@@ -350,7 +350,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* o_free = o_full + 2;                 // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int nqt = (T + 127) / 128;
   const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
   int total_steps = 0;
@@ -381,7 +381,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;  // S buffers at columns [0,64) and [64,128); O buffers at [128,192) and [192,256)
+  const uint32_t tmem_base = ptx::uniform(*tmem_slot);  // S buffers at columns [0,64) and [64,128); O buffers at [128,192) and [192,256)
 
   // number of 64-row K/V tiles of an item
   auto tiles_of = [&](int it) {
@@ -413,7 +413,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = ptx::elect_one();  // the whole warp runs this loop (uniform operands); one elected lane issues
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(128, 64, 0, 1);
       const uint32_t sQ = ptx::smem_u32(smem + FwdSmem::Q);
@@ -428,9 +429,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::tc_fence_after();
         const uint32_t sQi = sQ + (s_k & 1) * 16384, sK = sKV + (s_gt % kFwdRing) * 16384;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ss(tmem_base + (s_gt & 1) * 64, desc_k(sQi, k), desc_k(sK, k), idesc_s, k > 0);
-        ptx::umma_commit(&s_full[s_gt & 1]);
-        if (s_j == s_n - 1) ptx::umma_commit(&q_empty[s_k & 1]);  // last S of the item: its Q tile may be overwritten
+        for (int k = 0; k < 4; ++k) if (leader) ptx::umma_ss(tmem_base + (s_gt & 1) * 64, desc_k(sQi, k), desc_k(sK, k), idesc_s, k > 0);
+        if (leader) ptx::umma_commit(&s_full[s_gt & 1]);
+        if (leader && (s_j == s_n - 1)) ptx::umma_commit(&q_empty[s_k & 1]);  // last S of the item: its Q tile may be overwritten
         ++s_j;
         ++s_gt;
         if (s_j == s_n) {
@@ -450,10 +451,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t tP = tmem_base + (p_gt & 1) * 64;  // bf16 P (32 packed columns) written over the consumed S tile
         const uint32_t tO = tmem_base + 128 + (p_k & 1) * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_ts(tO, tP + 8 * k, desc_mn(sV, k), idesc_o, (p_j > 0 || k > 0));
-        ptx::umma_commit(&kv_empty[p_gt % kFwdRing]);
-        ptx::umma_commit(&p_empty[p_gt & 1]);
-        if (p_j == p_n - 1) ptx::umma_commit(&o_full[p_k & 1]);
+        for (int k = 0; k < 4; ++k) if (leader) ptx::umma_ts(tO, tP + 8 * k, desc_mn(sV, k), idesc_o, (p_j > 0 || k > 0));
+        if (leader) ptx::umma_commit(&kv_empty[p_gt % kFwdRing]);
+        if (leader) ptx::umma_commit(&p_empty[p_gt & 1]);
+        if (leader && (p_j == p_n - 1)) ptx::umma_commit(&o_full[p_k & 1]);
         ++p_j;
         ++p_gt;
         if (p_j == p_n) {
@@ -667,7 +668,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   uint64_t* acc_free = acc_full + 2;            // [2] ... and drained into registers by all 256 compute threads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int nqt = (T + 127) / 128;
   int total_steps = 0;
 
@@ -699,7 +700,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = ptx::uniform(*tmem_slot);
   const uint32_t tm_dQ = tmem_base + 128 * kSBuf;  // score buffer b: S at 128 b, dP at 128 b + 64; dQ buffers at 384, 448
 
   // number of 64-row K/V tiles of an item (item -> query tile nqt-1-rank: heaviest first)
@@ -735,7 +736,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   } else if (warp == 1) {
     // ---- score MMAs: S_j = Q K_j^T, dP_j = dO V_j^T into TMEM score buffer gs % kSBuf (one issuing thread per MMA
     // family: a single thread issuing all twelve MMAs of a step plus its barrier traffic was the bottleneck)
-    if (lane == 0) {
+    {
+      const bool leader = ptx::elect_one();  // the whole warp runs this loop (uniform operands); one elected lane issues
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0, 0);
       const uint64_t dQDO0 = desc_k(ptx::smem_u32(smem + DqSmem::QDO), 0);
       const uint64_t dKV0 = desc_k(ptx::smem_u32(smem + DqSmem::KV), 0);
@@ -753,18 +755,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
           const uint64_t dK = dKV0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4)), dV = dK + (8192 >> 4);
           const uint32_t tS = tmem_base + (gs % kSBuf) * 128;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_ss(tS, dQ0 + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ss(tS, dQ0 + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_ss(tS + 64, dDO0 + 2 * kk, dV + 2 * kk, idesc_s, kk > 0);
-          ptx::umma_commit(&s_full[gs % kSBuf]);
+          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ss(tS + 64, dDO0 + 2 * kk, dV + 2 * kk, idesc_s, kk > 0);
+          if (leader) ptx::umma_commit(&s_full[gs % kSBuf]);
         }
-        ptx::umma_commit(&qdo_empty[k & 1]);  // all score MMAs of the item done: its Q / dO tiles may be overwritten
+        if (leader) ptx::umma_commit(&qdo_empty[k & 1]);  // all score MMAs of the item done: its Q / dO tiles may be overwritten
       }
     }
     __syncwarp();
   } else if (warp == 10) {
     // ---- accumulating MMAs: dQ += dS_j K_j  (dQ accumulator double-buffered by item parity)
-    if (lane == 0) {
+    {
+      const bool leader = ptx::elect_one();  // the whole warp runs this loop (uniform operands); one elected lane issues
       constexpr uint32_t idesc_dq = ptx::umma_idesc_bf16(128, 64, 0, 1);
       const uint64_t dKmn0 = desc_mn(ptx::smem_u32(smem + DqSmem::KV), 0);
       int gs = 0;
@@ -784,11 +787,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
           const uint32_t tA = tmem_base + (gs % kSBuf) * 128;
           const uint64_t dK = dKmn0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_ts(tAcc, tA + 8 * kk, dK + (2048 >> 4) * kk, idesc_dq, (j > 0 || kk > 0));
-          ptx::umma_commit(&kv_empty[gs % kRing]);  // S_j / dP_j (other issuer) completed before ds_full could complete
-          ptx::umma_commit(&s_free[gs % kSBuf]);    // the score buffer (now holding dS) may be overwritten
+          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ts(tAcc, tA + 8 * kk, dK + (2048 >> 4) * kk, idesc_dq, (j > 0 || kk > 0));
+          if (leader) ptx::umma_commit(&kv_empty[gs % kRing]);  // S_j / dP_j (other issuer) completed before ds_full could complete
+          if (leader) ptx::umma_commit(&s_free[gs % kSBuf]);    // the score buffer (now holding dS) may be overwritten
         }
-        ptx::umma_commit(&acc_full[k & 1]);
+        if (leader) ptx::umma_commit(&acc_full[k & 1]);
       }
     }
     __syncwarp();
@@ -946,7 +949,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
   float* stat = reinterpret_cast<float*>(smem + DkvSmem::STAT);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int nq64 = (T + 63) / 64;
   int total_steps = 0;
 
@@ -978,7 +981,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = ptx::uniform(*tmem_slot);
   const uint32_t tm_dV = tmem_base + 128 * kSBuf, tm_dK = tm_dV + 64;  // score buffer b: S^T at 128 b, dP^T at 128 b + 64
 
   // item -> key tile kt = rank (tile 0 sees every query tile: heaviest first); steps = 64-row query tiles from 2 kt on
@@ -1010,7 +1013,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     __syncwarp();
   } else if (warp == 1) {
     // ---- score MMAs: S^T_n = K Q_n^T, dP^T_n = V dO_n^T into TMEM score buffer gs % kSBuf
-    if (lane == 0) {
+    {
+      const bool leader = ptx::elect_one();  // the whole warp runs this loop (uniform operands); one elected lane issues
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0, 0);
       const uint64_t dKV0 = desc_k(ptx::smem_u32(smem + DkvSmem::KV), 0);
       const uint64_t dQDO0 = desc_k(ptx::smem_u32(smem + DkvSmem::QDO), 0);
@@ -1028,18 +1032,19 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
           const uint64_t dQ = dQDO0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
           const uint32_t tS = tmem_base + (gs % kSBuf) * 128;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_ss(tS, dK0 + 2 * kk, dQ + 2 * kk, idesc_s, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ss(tS, dK0 + 2 * kk, dQ + 2 * kk, idesc_s, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_ss(tS + 64, dV0 + 2 * kk, dDO + 2 * kk, idesc_s, kk > 0);
-          ptx::umma_commit(&s_full[gs % kSBuf]);
+          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ss(tS + 64, dV0 + 2 * kk, dDO + 2 * kk, idesc_s, kk > 0);
+          if (leader) ptx::umma_commit(&s_full[gs % kSBuf]);
         }
-        ptx::umma_commit(&kv_empty[k & 1]);  // all score MMAs of the item done: its K / V tiles may be overwritten
+        if (leader) ptx::umma_commit(&kv_empty[k & 1]);  // all score MMAs of the item done: its K / V tiles may be overwritten
       }
     }
     __syncwarp();
   } else if (warp == 10) {
     // ---- accumulating MMAs: dV += P^T_n dO_n, dK += dS^T_n Q_n
-    if (lane == 0) {
+    {
+      const bool leader = ptx::elect_one();  // the whole warp runs this loop (uniform operands); one elected lane issues
       constexpr uint32_t idesc_g = ptx::umma_idesc_bf16(128, 64, 0, 1);
       const uint64_t dQmn0 = desc_mn(ptx::smem_u32(smem + DkvSmem::QDO), 0);
       int gs = 0;
@@ -1057,13 +1062,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
           const uint32_t tP = tmem_base + (gs % kSBuf) * 128, tDS = tP + 64;  // bf16 pairs written over the consumed scores
           const uint64_t dQ = dQmn0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4)), dDO = dQ + (8192 >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_ts(tm_dV, tP + 8 * kk, dDO + (2048 >> 4) * kk, idesc_g, (n > 0 || kk > 0));
+          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ts(tm_dV, tP + 8 * kk, dDO + (2048 >> 4) * kk, idesc_g, (n > 0 || kk > 0));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_ts(tm_dK, tDS + 8 * kk, dQ + (2048 >> 4) * kk, idesc_g, (n > 0 || kk > 0));
-          ptx::umma_commit(&qdo_empty[gs % kRing]);
-          ptx::umma_commit(&s_free[gs % kSBuf]);
+          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ts(tm_dK, tDS + 8 * kk, dQ + (2048 >> 4) * kk, idesc_g, (n > 0 || kk > 0));
+          if (leader) ptx::umma_commit(&qdo_empty[gs % kRing]);
+          if (leader) ptx::umma_commit(&s_free[gs % kSBuf]);
         }
-        ptx::umma_commit(acc_full);
+        if (leader) ptx::umma_commit(acc_full);
       }
     }
     __syncwarp();
@@ -1292,4 +1297,55 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
   return launch_status("attn_bwd_dq_kernel");
 }
 
+}  // namespace abcgpt
+
+// ---- debug micro-benchmark: tcgen05.ld throughput / latency (tools/tmem_bench.py) -------------------------------------
+namespace abcgpt {
+namespace {
+template <int INFLIGHT>
+__global__ void __launch_bounds__(256, 1) tmem_ld_bench_kernel(long long* out, int iters, int nwarps) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    ptx::tmem_alloc(&slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t base = slot + (static_cast<uint32_t>((warp & 3) * 32) << 16) + (warp >> 2) * 256;
+  uint32_t acc = 0;
+  long long t0 = 0, t1 = 0;
+  if (warp < nwarps) {
+    uint32_t v[32], w[32], x[32], y[32];
+    t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      ptx::tmem_ld32(base, v);
+      if (INFLIGHT >= 2) ptx::tmem_ld32(base + 32, w);
+      if (INFLIGHT >= 4) {
+        ptx::tmem_ld32(base + 64, x);
+        ptx::tmem_ld32(base + 96, y);
+      }
+      ptx::tmem_ld_wait();
+      acc += v[0] ^ v[13] ^ v[31];
+      if (INFLIGHT >= 2) acc += w[0] ^ w[13] ^ w[31];
+      if (INFLIGHT >= 4) acc += (x[0] ^ x[13] ^ x[31]) + (y[0] ^ y[13] ^ y[31]);
+    }
+    t1 = clock64();
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && warp < nwarps) {
+    out[blockIdx.x * 8 + warp] = t1 - t0 + (acc == 0x12345u ? 1 : 0);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(slot, 512);
+}
+}  // namespace
+int tmem_ld_bench(long long* out, int iters, int nwarps, int inflight, cudaStream_t stream) {
+  if (inflight >= 4) tmem_ld_bench_kernel<4><<<1, 256, 0, stream>>>(out, iters, nwarps);
+  else if (inflight >= 2) tmem_ld_bench_kernel<2><<<1, 256, 0, stream>>>(out, iters, nwarps);
+  else tmem_ld_bench_kernel<1><<<1, 256, 0, stream>>>(out, iters, nwarps);
+  return launch_status("tmem_ld_bench_kernel");
+}
 }  // namespace abcgpt

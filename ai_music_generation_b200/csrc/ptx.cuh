@@ -255,6 +255,25 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
 }
 
 // ----------------------------------------------------------------------------------------------
+// Warp-uniform issue.  tcgen05.mma / tcgen05.commit take their operands in UNIFORM registers.  If the issuing code sits
+// in a divergent region (`if (lane == 0) { ... }`) ptxas cannot prove the operands uniform and wraps every MMA in an
+// ELECT / 5 x R2UR.BROADCAST / branch "waterfall" (~100 cycles of issue per instruction, measured: three times the
+// execution time of a 128x64x16 MMA).  Instead the WHOLE warp runs the issue loop (uniform control flow, values derived
+// from kernel parameters / blockIdx / __shfl_sync broadcasts) and only the instruction itself is predicated on one
+// elected lane.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// ----------------------------------------------------------------------------------------------
 // Descriptors
 // ----------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (Blackwell).

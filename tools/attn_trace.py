@@ -30,7 +30,7 @@ dqkv = torch.empty(B * T, 3 * C, device="cuda", dtype=torch.bfloat16)
 delta = torch.empty(B, H, T, device="cuda")
 for _ in range(2):
     ops.attn_bwd(qkv, o, do, lse, delta, dqkv, B, T, H)
-tr2 = torch.zeros(1024, device="cuda", dtype=torch.int64)
+tr2 = torch.zeros(2048, device="cuda", dtype=torch.int64)
 _C.lib().abcgpt_debug_attn_trace(tr2.data_ptr())
 ops.attn_bwd(qkv, o, do, lse, delta, dqkv, B, T, H)
 torch.cuda.synchronize()
@@ -46,3 +46,9 @@ for name, base in (("dq", 0), ("dkv", 512)):
         print(j, int(r[5]), int(r[6]), "|", (r[1] - r[0]).item(), (r[2] - r[1]).item(), (r[3] - r[2]).item(), (r[4] - r[3]).item(), "|",
               (r[4] - r[0]).item(), "|", (r[0] - prev).item() if prev is not None else 0)
         prev = r[0]
+
+m = tr2[1024:1024 + 256].view(64, 4).cpu()
+print("dq issuer step: wait_dS  acc_issue  score_issue(incl. kv wait) | since previous")
+for j in range(40):
+    r = m[j]
+    print(j, (r[1] - r[0]).item(), (r[2] - r[1]).item(), (r[3] - r[2]).item(), "|", (r[0] - m[j - 1][0]).item() if j else 0)
