@@ -390,7 +390,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool issue = ptx::elect_one();  // whole warp runs the loop, one elected lane issues (uniform operands)
       int gt = 0;
       for (int item_k = 0;; ++item_k) {
         const int it = sched_item(item_k, nitems);
@@ -399,15 +400,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int num_kv = tiles_of(it);
         const int qb = item_k & 1;
         ptx::mbar_wait(&q_empty[qb], ((item_k >> 1) & 1) ^ 1, 10);
-        ptx::mbar_expect_tx(&q_full[qb], 16384);
-        ptx::tma_load_2d(smem + FwdSmem::Q + qb * 16384, &tmQ, &q_full[qb], h * HS, b * T + qt * 128);
+        if (issue) ptx::mbar_expect_tx(&q_full[qb], 16384);
+        if (issue) ptx::tma_load_2d(smem + FwdSmem::Q + qb * 16384, &tmQ, &q_full[qb], h * HS, b * T + qt * 128);
         for (int j = 0; j < num_kv; ++j, ++gt) {
           const int st = gt % kFwdRing;
           ptx::mbar_wait(&kv_empty[st], ((gt / kFwdRing) & 1) ^ 1, 11);
-          ptx::mbar_expect_tx(&kv_full[st], 16384);
+          if (issue) ptx::mbar_expect_tx(&kv_full[st], 16384);
           uint8_t* dst = smem + FwdSmem::KV + st * 16384;
-          ptx::tma_load_2d(dst, &tmKV, &kv_full[st], C + h * HS, b * T + j * 64);
-          ptx::tma_load_2d(dst + 8192, &tmKV, &kv_full[st], 2 * C + h * HS, b * T + j * 64);
+          if (issue) ptx::tma_load_2d(dst, &tmKV, &kv_full[st], C + h * HS, b * T + j * 64);
+          if (issue) ptx::tma_load_2d(dst + 8192, &tmKV, &kv_full[st], 2 * C + h * HS, b * T + j * 64);
         }
       }
     }
@@ -710,7 +711,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool issue = ptx::elect_one();  // whole warp runs the loop, one elected lane issues (uniform operands)
       int gs = 0;
       for (int k = 0;; ++k) {
         const int it = sched_item(k, nitems);
@@ -719,16 +721,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
         const int num_kv = tiles_of(it), row0 = b * T + qt * 128;
         const int qb = k & 1;
         ptx::mbar_wait(&qdo_empty[qb], ((k >> 1) & 1) ^ 1, 20);
-        ptx::mbar_expect_tx(&qdo_full[qb], 32768);
-        ptx::tma_load_2d(smem + DqSmem::QDO + qb * 32768, &tmQKV128, &qdo_full[qb], h * HS, row0);
-        ptx::tma_load_2d(smem + DqSmem::QDO + qb * 32768 + 16384, &tmDO128, &qdo_full[qb], h * HS, row0);
+        if (issue) ptx::mbar_expect_tx(&qdo_full[qb], 32768);
+        if (issue) ptx::tma_load_2d(smem + DqSmem::QDO + qb * 32768, &tmQKV128, &qdo_full[qb], h * HS, row0);
+        if (issue) ptx::tma_load_2d(smem + DqSmem::QDO + qb * 32768 + 16384, &tmDO128, &qdo_full[qb], h * HS, row0);
         for (int j = 0; j < num_kv; ++j, ++gs) {
           const int st = gs % kRing;
           ptx::mbar_wait(&kv_empty[st], ((gs / kRing) & 1) ^ 1, 21);
-          ptx::mbar_expect_tx(&kv_full[st], 16384);
+          if (issue) ptx::mbar_expect_tx(&kv_full[st], 16384);
           uint8_t* dst = smem + DqSmem::KV + st * 16384;
-          ptx::tma_load_2d(dst, &tmQKV64, &kv_full[st], C + h * HS, b * T + j * 64);
-          ptx::tma_load_2d(dst + 8192, &tmQKV64, &kv_full[st], 2 * C + h * HS, b * T + j * 64);
+          if (issue) ptx::tma_load_2d(dst, &tmQKV64, &kv_full[st], C + h * HS, b * T + j * 64);
+          if (issue) ptx::tma_load_2d(dst + 8192, &tmQKV64, &kv_full[st], 2 * C + h * HS, b * T + j * 64);
         }
       }
     }
@@ -988,7 +990,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   auto steps_of = [&](int it) { return nq64 - (it / BH) * 2; };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool issue = ptx::elect_one();  // whole warp runs the loop, one elected lane issues (uniform operands)
       int gs = 0;
       for (int k = 0;; ++k) {
         const int it = sched_item(k, nitems);
@@ -997,16 +1000,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         const int i0 = kt * 2, nq = steps_of(it);
         const int kb = k & 1;
         ptx::mbar_wait(&kv_empty[kb], ((k >> 1) & 1) ^ 1, 30);
-        ptx::mbar_expect_tx(&kv_full[kb], 32768);
-        ptx::tma_load_2d(smem + DkvSmem::KV + kb * 32768, &tmQKV128, &kv_full[kb], C + h * HS, b * T + kt * 128);
-        ptx::tma_load_2d(smem + DkvSmem::KV + kb * 32768 + 16384, &tmQKV128, &kv_full[kb], 2 * C + h * HS, b * T + kt * 128);
+        if (issue) ptx::mbar_expect_tx(&kv_full[kb], 32768);
+        if (issue) ptx::tma_load_2d(smem + DkvSmem::KV + kb * 32768, &tmQKV128, &kv_full[kb], C + h * HS, b * T + kt * 128);
+        if (issue) ptx::tma_load_2d(smem + DkvSmem::KV + kb * 32768 + 16384, &tmQKV128, &kv_full[kb], 2 * C + h * HS, b * T + kt * 128);
         for (int n = 0; n < nq; ++n, ++gs) {
           const int st = gs % kRing;
           ptx::mbar_wait(&qdo_empty[st], ((gs / kRing) & 1) ^ 1, 31);
-          ptx::mbar_expect_tx(&qdo_full[st], 16384);
+          if (issue) ptx::mbar_expect_tx(&qdo_full[st], 16384);
           uint8_t* dst = smem + DkvSmem::QDO + st * 16384;
-          ptx::tma_load_2d(dst, &tmQKV64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
-          ptx::tma_load_2d(dst + 8192, &tmDO64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
+          if (issue) ptx::tma_load_2d(dst, &tmQKV64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
+          if (issue) ptx::tma_load_2d(dst + 8192, &tmDO64, &qdo_full[st], h * HS, b * T + (i0 + n) * 64);
         }
       }
     }

@@ -247,7 +247,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = ptx::uniform(threadIdx.x >> 5);  // provably warp-uniform: the issuer loops below stay on the uniform datapath
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -270,7 +270,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = ptx::uniform(*tmem_slot);
 
   const int total_work = p.num_m_blk * p.num_n_blk * p.splits;
   const long long t_start = p.stats ? clock64() : 0;
@@ -278,7 +278,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
+      const bool issue = ptx::elect_one();  // whole warp runs the loop, one elected lane issues (uniform operands)
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -290,22 +291,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           timed_wait(&empty[stage], phase ^ 1, 1, p.stats, 0, w0);
-          ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          if (issue) ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           if constexpr (!A_MN) {
-            ptx::tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
+            if (issue) ptx::tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
           } else {
 #pragma unroll
             for (int a = 0; a < BM / 64; ++a)
-              ptx::tma_load_2d(sa + a * (BK * 128), &tmA, &full[stage], m_blk * BM + a * 64, kb * BK);
+              if (issue) ptx::tma_load_2d(sa + a * (BK * 128), &tmA, &full[stage], m_blk * BM + a * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            ptx::tma_load_2d(sb, &tmB, &full[stage], kb * BK, n_blk * BN);
+            if (issue) ptx::tma_load_2d(sb, &tmB, &full[stage], kb * BK, n_blk * BN);
           } else {
 #pragma unroll
             for (int b = 0; b < BN / 64; ++b)
-              ptx::tma_load_2d(sb + b * (BK * 128), &tmB, &full[stage], n_blk * BN + b * 64, kb * BK);
+              if (issue) ptx::tma_load_2d(sb + b * (BK * 128), &tmB, &full[stage], n_blk * BN + b * 64, kb * BK);
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -313,12 +314,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
-      if (p.stats) atomicAdd(&p.stats[0], static_cast<unsigned long long>(w0));
+      if (issue && p.stats) atomicAdd(&p.stats[0], static_cast<unsigned long long>(w0));
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
+      // the whole warp runs the loop (uniform operands, see ptx::elect_one); one elected lane issues
+      const bool issue = ptx::elect_one();
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -345,17 +348,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : ptx::umma_smem_desc(a_base + k * 32, 0, 1024);
             const uint64_t bdesc = B_MN ? ptx::umma_smem_desc(b_base + k * 2048, BK * 128, 1024)
                                         : ptx::umma_smem_desc(b_base + k * 32, 0, 1024);
-            ptx::umma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (issue) ptx::umma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (issue) ptx::umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit(&tfull[as]);  // accumulator complete
+        if (issue) ptx::umma_commit(&tfull[as]);  // accumulator complete
       }
-      if (p.stats) {
+      if (issue && p.stats) {
         atomicAdd(&p.stats[1], static_cast<unsigned long long>(w0));
         atomicAdd(&p.stats[2], static_cast<unsigned long long>(w1));
       }
@@ -474,7 +477,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = ptx::uniform(threadIdx.x >> 5);  // provably warp-uniform: the issuer loops below stay on the uniform datapath
   const int lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
@@ -499,7 +502,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   ptx::tc_fence_before();
   ptx::cluster_sync_all();  // barrier inits + TMEM allocations of BOTH CTAs are visible before anything is signalled
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = ptx::uniform(*tmem_slot);
 
   const int num_m_pair = (p.num_m_blk + 1) / 2;
   const int total_work = num_m_pair * p.num_n_blk * p.splits;
@@ -508,7 +511,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    {
+      const bool issue = ptx::elect_one();  // whole warp runs the loop, one elected lane issues (uniform operands)
       int stage = 0;
       uint32_t phase = 0;
       for (int w = pair_id; w < total_work; w += num_pairs) {
@@ -521,20 +525,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1, 41);
           const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
-          if (leader) ptx::mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+          if (leader && issue) ptx::mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           if constexpr (!A_MN) {
-            ptx::tma_load_2d_2sm(sa, &tmA, full_leader, kb * BK, m0);
+            if (issue) ptx::tma_load_2d_2sm(sa, &tmA, full_leader, kb * BK, m0);
           } else {
 #pragma unroll
-            for (int a = 0; a < 2; ++a) ptx::tma_load_2d_2sm(sa + a * (BK * 128), &tmA, full_leader, m0 + a * 64, kb * BK);
+            for (int a = 0; a < 2; ++a) if (issue) ptx::tma_load_2d_2sm(sa + a * (BK * 128), &tmA, full_leader, m0 + a * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            ptx::tma_load_2d_2sm(sb, &tmB, full_leader, kb * BK, n0);
+            if (issue) ptx::tma_load_2d_2sm(sb, &tmB, full_leader, kb * BK, n0);
           } else {
 #pragma unroll
-            for (int b = 0; b < 2; ++b) ptx::tma_load_2d_2sm(sb + b * (BK * 128), &tmB, full_leader, n0 + b * 64, kb * BK);
+            for (int b = 0; b < 2; ++b) if (issue) ptx::tma_load_2d_2sm(sb + b * (BK * 128), &tmB, full_leader, n0 + b * 64, kb * BK);
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -546,7 +550,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) {
+      // the whole warp runs the loop (uniform operands, see ptx::elect_one); one elected lane issues
+      const bool issue = ptx::elect_one();
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -571,15 +577,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                         : ptx::umma_smem_desc(a_base + k * 32, 0, 1024);
             const uint64_t bdesc = B_MN ? ptx::umma_smem_desc(b_base + k * 2048, BK * 128, 1024)
                                         : ptx::umma_smem_desc(b_base + k * 32, 0, 1024);
-            ptx::umma_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (issue) ptx::umma_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit_2sm(&empty[stage], 3);
+          if (issue) ptx::umma_commit_2sm(&empty[stage], 3);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit_2sm(&tfull[as], 3);
+        if (issue) ptx::umma_commit_2sm(&tfull[as], 3);
       }
     }
     __syncwarp();
