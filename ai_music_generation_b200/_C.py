@@ -42,6 +42,7 @@ _SIGNATURES = {
     "abcgpt_debug_gemm_stats": (c_int, [_P]),
     "abcgpt_debug_attn_trace": (c_int, [_P]),
     "abcgpt_debug_attn_cta_trace": (c_int, [_P]),
+    "abcgpt_debug_mma_bench": (c_int, [_P, c_int, c_int, c_int, _P]),
     "abcgpt_debug_tmem_ld_bench": (c_int, [_P, c_int, c_int, c_int, _P]),
     "abcgpt_argmax": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P]),
 }

@@ -4,7 +4,7 @@
 #include "kernels.h"
 
 using namespace abcgpt;
-namespace abcgpt { extern unsigned long long* g_gemm_stats; extern long long* g_attn_trace; extern long long* g_attn_cta_trace; int tmem_ld_bench(long long*, int, int, int, cudaStream_t); }
+namespace abcgpt { extern unsigned long long* g_gemm_stats; extern long long* g_attn_trace; extern long long* g_attn_cta_trace; int tmem_ld_bench(long long*, int, int, int, cudaStream_t); int mma_bench(long long*, int, int, int, cudaStream_t); int mma2_bench(long long*, int, int, cudaStream_t); }
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
 
@@ -103,6 +103,12 @@ int abcgpt_debug_attn_cta_trace(void* device_records) {
 /* debug: cycles of `iters` x (inflight x tcgen05.ld 32x32b.x32 + wait) on nwarps warps of one CTA; out[warp] */
 int abcgpt_debug_tmem_ld_bench(void* out, int iters, int nwarps, int inflight, void* stream) {
   return abcgpt::tmem_ld_bench(reinterpret_cast<long long*>(out), iters, nwarps, inflight, S(stream));
+}
+
+/* debug: cycles of 4 x iters tcgen05.mma 128 x n x 16 (mode: A 0 smem K-major / 1 smem MN-major / 2 TMEM; +4 B MN-major) */
+int abcgpt_debug_mma_bench(void* out, int iters, int n, int mode, void* stream) {
+  if (mode < 0) return abcgpt::mma2_bench(reinterpret_cast<long long*>(out), iters, n, S(stream));  /* CTA pair, 256 x n x 16 */
+  return abcgpt::mma_bench(reinterpret_cast<long long*>(out), iters, n, mode, S(stream));
 }
 
 int abcgpt_debug_attn_trace(void* device_stamps) {

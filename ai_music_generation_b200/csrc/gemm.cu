@@ -56,42 +56,45 @@ struct Cfg {
 };
 
 // ---- GELU (exact-erf form of nn.GELU(), model.py:83) ---------------------------------------------------
-// Phi(x) = 0.5 (1 + erf(x / sqrt2)) with erf(z) = z * P(t), t = 2 z^2 / 3.5^2 - 1, |z| clamped to 3.5 (erf(3.5) = 1 - 7e-7):
-// a degree-12 Chebyshev-derived polynomial, |Phi error| < 4e-7 in fp32 (the class of erff itself), evaluated on
-// the packed fp32x2 FMA pipe for two columns at a time.  No MUFU in the forward; the backward adds one ex2 per
-// element for the Gaussian pdf.  The epilogue warps are issue-bound, so instruction count is what matters here.
-__device__ __forceinline__ float2 gelu_cdf2(float2 x) {
-  const float2 z = __fmul2_rn(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
-  const float2 zc = make_float2(fminf(fmaxf(z.x, -3.5f), 3.5f), fminf(fmaxf(z.y, -3.5f), 3.5f));
-  const float2 t = __ffma2_rn(__fmul2_rn(zc, zc), make_float2(0.16326530612244897f, 0.16326530612244897f),
-                              make_float2(-1.0f, -1.0f));
-  float2 acc = make_float2(1.783549204e-03f, 1.783549204e-03f);
+// Evaluated on the packed fp32x2 FMA pipe for two columns at a time; the epilogue warps are issue-bound, so instruction count
+// is what matters here.
+// Phi(x) = 0.5 erfc(-x / sqrt 2) through Abramowitz-Stegun 7.1.26: erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),
+// t = 1 / (1 + p z), z >= 0 (|error| < 1.5e-7; measured |dPhi| < 3e-7 in fp32 with the approximate MUFU reciprocal / exponential,
+// the class of erff itself).  The negative side is 0.5 erfc(z) directly (no cancellation: ~1e-3 relative accuracy far
+// into the tail), the positive side 1 - 0.5 erfc(z).  exp(-z^2) = exp(-x^2 / 2) is also the Gaussian of the GELU derivative,
+// so the backward epilogue gets its pdf for free.  15 instructions + 4 MUFU per column pair against 26 for the degree-12
+// polynomial this replaces: the GELU / GELU' epilogues were the bottleneck of their GEMMs (accumulator-empty waits of
+// 25-40 % on the MMA issuer, tools/gemm_stats.py).
+__device__ __forceinline__ float2 gelu_cdf2(float2 x, float2& e) {
+  const float2 az = make_float2(fabsf(x.x) * 0.70710678118654752f, fabsf(x.y) * 0.70710678118654752f);
+  const float2 d = __ffma2_rn(az, make_float2(0.3275911f, 0.3275911f), make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+  const float2 arg = __fmul2_rn(__fmul2_rn(x, x), make_float2(-0.72134752044448170f, -0.72134752044448170f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));  // exp(-x^2 / 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
+  // coefficients pre-multiplied by 0.5
+  float2 acc = make_float2(0.5307027145f, 0.5307027145f);
 #define ABCGPT_HORNER(c) acc = __ffma2_rn(acc, t, make_float2(c, c))
-  ABCGPT_HORNER(-4.138993458e-03f);
-  ABCGPT_HORNER(3.642286241e-03f);
-  ABCGPT_HORNER(-6.848857084e-03f);
-  ABCGPT_HORNER(1.790029780e-02f);
-  ABCGPT_HORNER(-3.037289646e-02f);
-  ABCGPT_HORNER(4.461858910e-02f);
-  ABCGPT_HORNER(-6.463799105e-02f);
-  ABCGPT_HORNER(8.848482037e-02f);
-  ABCGPT_HORNER(-1.146334766e-01f);
-  ABCGPT_HORNER(1.467439851e-01f);
-  ABCGPT_HORNER(-2.007001497e-01f);
-  ABCGPT_HORNER(4.038730577e-01f);
+  ABCGPT_HORNER(-0.7265760135f);
+  ABCGPT_HORNER(0.7107068705f);
+  ABCGPT_HORNER(-0.142248368f);
+  ABCGPT_HORNER(0.127414796f);
 #undef ABCGPT_HORNER
-  const float2 e = __fmul2_rn(zc, acc);
-  return __ffma2_rn(e, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  const float2 hq = __fmul2_rn(__fmul2_rn(acc, t), e);  // 0.5 erfc(|x| / sqrt 2)
+  const float2 up = __ffma2_rn(hq, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));
+  return make_float2(x.x >= 0.f ? up.x : hq.x, x.y >= 0.f ? up.y : hq.y);
 }
-__device__ __forceinline__ float2 gelu_fwd2(float2 x) { return __fmul2_rn(x, gelu_cdf2(x)); }
+__device__ __forceinline__ float2 gelu_fwd2(float2 x) {
+  float2 e;
+  return __fmul2_rn(x, gelu_cdf2(x, e));
+}
 __device__ __forceinline__ float2 gelu_bwd2(float2 x) {
-  const float2 cdf = gelu_cdf2(x);
-  const float2 xx = __fmul2_rn(x, x);
-  // pdf = exp(-x^2/2) / sqrt(2 pi) = 2^(-x^2 * 0.5 log2e) * 0.39894228
-  float2 pdf;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pdf.x) : "f"(xx.x * -0.72134752044448170f));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pdf.y) : "f"(xx.y * -0.72134752044448170f));
-  pdf = __fmul2_rn(pdf, make_float2(0.39894228040143268f, 0.39894228040143268f));
+  float2 e;
+  const float2 cdf = gelu_cdf2(x, e);
+  // pdf = exp(-x^2/2) / sqrt(2 pi)
+  const float2 pdf = __fmul2_rn(e, make_float2(0.39894228040143268f, 0.39894228040143268f));
   return __ffma2_rn(x, pdf, cdf);
 }
 
@@ -464,10 +467,16 @@ struct Cfg2 {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 };
 
-template <bool A_MN, bool B_MN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+// QUAD: clusters of FOUR CTAs = two CTA pairs working on vertically adjacent 256-row tiles of the same 256 output columns.
+// Both pairs need the same B (weight) k-blocks, so each CTA fetches only HALF of its 128 B rows and multicasts them to the
+// CTA with the same role in the other pair: the L2 -> SM operand traffic per FLOP drops by a quarter.  That traffic is what
+// bounds this GEMM: a CTA pair issues 256x256x16 MMAs at the math rate (128 cycles, tools/mma_bench.py) but needs 64 B/clk
+// of operands per SM, 9.5 KB/clk chip-wide against ~6.3 KB/clk of L2 -> SM delivery: pairs alone top out at ~2/3 of peak.
+template <bool A_MN, bool B_MN, int EPI, bool QUAD>
+__global__ void __launch_bounds__(kNumThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using C = Cfg2;
+  constexpr int CL = QUAD ? 4 : 2;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -479,7 +488,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = ptx::uniform(threadIdx.x >> 5);  // provably warp-uniform: the issuer loops below stay on the uniform datapath
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t crank = ptx::cluster_ctarank();  // rank in the cluster
+  const uint32_t rank = crank & 1;                // CTA within its pair
+  const uint32_t pr = crank >> 1;                 // pair within the cluster (QUAD: 0 / 1)
   const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
@@ -487,7 +498,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < C::STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&empty[s], QUAD ? 2 : 1);  // QUAD: a stage is overwritten (multicast) only after BOTH pairs consumed it
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull[s], 1);
@@ -505,9 +516,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = ptx::uniform(*tmem_slot);
 
   const int num_m_pair = (p.num_m_blk + 1) / 2;
-  const int total_work = num_m_pair * p.num_n_blk * p.splits;
-  const int pair_id = blockIdx.x >> 1;
-  const int num_pairs = gridDim.x >> 1;
+  const int m_units = QUAD ? num_m_pair / 2 : num_m_pair;  // QUAD: the host guarantees an even number of 256-row tiles
+  const int total_work = m_units * p.num_n_blk * p.splits;
+  const int pair_id = blockIdx.x / CL;      // cluster index
+  const long long t_start = p.stats ? clock64() : 0;
+  long long w0 = 0, w1 = 0;
+  const int num_pairs = gridDim.x / CL;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -518,13 +532,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int w = pair_id; w < total_work; w += num_pairs) {
         const int split = w % p.splits;
         const int tile = w / p.splits;
-        const int m0 = (tile / p.num_n_blk) * 256 + static_cast<int>(rank) * 128;
+        const int m_unit = tile / p.num_n_blk;
+        const int m0 = (QUAD ? 2 * m_unit + static_cast<int>(pr) : m_unit) * 256 + static_cast<int>(rank) * 128;
         const int n0 = (tile % p.num_n_blk) * BN + static_cast<int>(rank) * (BN / 2);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
+        const uint16_t mc_mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));  // same role, both pairs
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1, 41);
-          const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+          timed_wait(&empty[stage], phase ^ 1, 41, p.stats, 0, w0);
+          const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full[stage]), crank & ~1u);  // own pair's leader
           if (leader && issue) ptx::mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
@@ -534,7 +550,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int a = 0; a < 2; ++a) if (issue) ptx::tma_load_2d_2sm(sa + a * (BK * 128), &tmA, full_leader, m0 + a * 64, kb * BK);
           }
-          if constexpr (!B_MN) {
+          if constexpr (QUAD) {
+            // this CTA's half (64 rows / 64 columns) of the B rows that its role needs, delivered to both pairs
+            if constexpr (!B_MN) {
+              if (issue) ptx::tma_load_2d_2sm_mc(sb + pr * 8192, &tmB, full_leader, kb * BK, n0 + static_cast<int>(pr) * 64, mc_mask);
+            } else {
+              if (issue) ptx::tma_load_2d_2sm_mc(sb + pr * (BK * 128), &tmB, full_leader, n0 + static_cast<int>(pr) * 64, kb * BK, mc_mask);
+            }
+          } else if constexpr (!B_MN) {
             if (issue) ptx::tma_load_2d_2sm(sb, &tmB, full_leader, kb * BK, n0);
           } else {
 #pragma unroll
@@ -546,6 +569,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      if (issue && p.stats) atomicAdd(&p.stats[0], static_cast<unsigned long long>(w0));
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -563,11 +587,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        ptx::mbar_wait(&tempty[as], aphase ^ 1, 42);
+        timed_wait(&tempty[as], aphase ^ 1, 42, p.stats, 2, w1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&full[stage], phase, 43);
+          timed_wait(&full[stage], phase, 43, p.stats, 1, w0);
           ptx::tc_fence_after();
           const uint32_t a_base = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_base = a_base + C::A_BYTES;
@@ -579,13 +603,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                         : ptx::umma_smem_desc(b_base + k * 32, 0, 1024);
             if (issue) ptx::umma_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (issue) ptx::umma_commit_2sm(&empty[stage], 3);
+          if (issue) ptx::umma_commit_2sm(&empty[stage], QUAD ? 0xF : 0x3);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (issue) ptx::umma_commit_2sm(&tfull[as], 3);
+        if (issue) ptx::umma_commit_2sm(&tfull[as], static_cast<uint16_t>(0x3u << (2 * pr)));
+      }
+      if (issue && p.stats) {
+        atomicAdd(&p.stats[1], static_cast<unsigned long long>(w0));
+        atomicAdd(&p.stats[2], static_cast<unsigned long long>(w1));
       }
     }
     __syncwarp();
@@ -597,7 +625,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int it = 0;
     for (int w = pair_id; w < total_work; w += num_pairs, ++it) {
       const int tile = w / p.splits;
-      const int m0 = (tile / p.num_n_blk) * 256 + static_cast<int>(rank) * 128;
+      const int m_unit = tile / p.num_n_blk;
+      const int m0 = (QUAD ? 2 * m_unit + static_cast<int>(pr) : m_unit) * 256 + static_cast<int>(rank) * 128;
       const int n_blk = tile % p.num_n_blk;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -607,7 +636,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       AuxChunk<EPI> aux[NCH];
 #pragma unroll
       for (int c = 0; c < NCH; ++c) load_aux<EPI>(aux[c], p, row, col_base + c * 32);
-      ptx::mbar_wait(&tfull[as], aphase, 44);
+      timed_wait(&tfull[as], aphase, 44, p.stats, 3, w0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
 #pragma unroll
@@ -619,7 +648,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[as]), 0));
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[as]), crank & ~1u));
+    }
+    if (p.stats && warp == 2 && lane == 0) {
+      atomicAdd(&p.stats[3], static_cast<unsigned long long>(w0));
+      atomicAdd(&p.stats[5], static_cast<unsigned long long>(clock64() - t_start));
     }
   }
 
@@ -628,37 +661,61 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
 }
 
-template <bool A_MN, bool B_MN, int EPI>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = gemm2_kernel<A_MN, B_MN, EPI>;
-  static bool configured = false;
-  if (!configured) {
+// Persistent launch with a cluster dimension attribute.  `units` = work items (one per cluster); the grid is the number of
+// clusters that can be co-resident (queried once per instantiation) or fewer.
+template <bool A_MN, bool B_MN, int EPI, bool QUAD>
+int launch2q(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, long long units, cudaStream_t stream) {
+  auto kern = gemm2_kernel<A_MN, B_MN, EPI, QUAD>;
+  constexpr int CL = QUAD ? 4 : 2;
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg2::SMEM_BYTES;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters == 0) {
     ABCGPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
-    configured = true;
+    cfg.gridDim = dim3(CL * (sm_count() / CL));
+    int n = 0;
+    ABCGPT_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    max_clusters = n > 0 ? n : 1;
   }
-  kern<<<grid, kNumThreads, Cfg2::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  const long long clusters = units < max_clusters ? units : max_clusters;
+  cfg.gridDim = dim3(static_cast<unsigned>(CL * clusters));
+  ABCGPT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   return launch_status("gemm2_kernel");
+}
+template <bool A_MN, bool B_MN, int EPI>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, long long units, bool quad, cudaStream_t stream) {
+  if (quad) return launch2q<A_MN, B_MN, EPI, true>(tmA, tmB, p, units, stream);
+  return launch2q<A_MN, B_MN, EPI, false>(tmA, tmB, p, units, stream);
 }
 
 template <bool A_MN, bool B_MN>
-int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, long long grid, bool quad,
                   cudaStream_t stream) {
   switch (epi) {
-    case ABCGPT_EPI_BF16: return launch2<A_MN, B_MN, ABCGPT_EPI_BF16>(tmA, tmB, p, grid, stream);
-    case ABCGPT_EPI_GELU: return launch2<A_MN, B_MN, ABCGPT_EPI_GELU>(tmA, tmB, p, grid, stream);
-    case ABCGPT_EPI_RESID: return launch2<A_MN, B_MN, ABCGPT_EPI_RESID>(tmA, tmB, p, grid, stream);
-    case ABCGPT_EPI_DGELU: return launch2<A_MN, B_MN, ABCGPT_EPI_DGELU>(tmA, tmB, p, grid, stream);
-    case ABCGPT_EPI_F32_RED: return launch2<A_MN, B_MN, ABCGPT_EPI_F32_RED>(tmA, tmB, p, grid, stream);
-    case ABCGPT_EPI_F32: return launch2<A_MN, B_MN, ABCGPT_EPI_F32>(tmA, tmB, p, grid, stream);
+    case ABCGPT_EPI_BF16: return launch2<A_MN, B_MN, ABCGPT_EPI_BF16>(tmA, tmB, p, grid, quad, stream);
+    case ABCGPT_EPI_GELU: return launch2<A_MN, B_MN, ABCGPT_EPI_GELU>(tmA, tmB, p, grid, quad, stream);
+    case ABCGPT_EPI_RESID: return launch2<A_MN, B_MN, ABCGPT_EPI_RESID>(tmA, tmB, p, grid, quad, stream);
+    case ABCGPT_EPI_DGELU: return launch2<A_MN, B_MN, ABCGPT_EPI_DGELU>(tmA, tmB, p, grid, quad, stream);
+    case ABCGPT_EPI_F32_RED: return launch2<A_MN, B_MN, ABCGPT_EPI_F32_RED>(tmA, tmB, p, grid, quad, stream);
+    case ABCGPT_EPI_F32: return launch2<A_MN, B_MN, ABCGPT_EPI_F32>(tmA, tmB, p, grid, quad, stream);
   }
   return fail(-1, "unknown GEMM epilogue %d", epi);
 }
 
 int dispatch_major2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                    int grid, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return dispatch_epi2<false, false>(epi, tmA, tmB, p, grid, stream);
-  if (!a_mn && b_mn) return dispatch_epi2<false, true>(epi, tmA, tmB, p, grid, stream);
-  if (a_mn && b_mn) return dispatch_epi2<true, true>(epi, tmA, tmB, p, grid, stream);
+                    long long grid, bool quad, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return dispatch_epi2<false, false>(epi, tmA, tmB, p, grid, quad, stream);
+  if (!a_mn && b_mn) return dispatch_epi2<false, true>(epi, tmA, tmB, p, grid, quad, stream);
+  if (a_mn && b_mn) return dispatch_epi2<true, true>(epi, tmA, tmB, p, grid, quad, stream);
   return fail(-1, "GEMM operand combination A=MN-major,B=K-major is not instantiated");
 }
 
@@ -691,12 +748,17 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
       bn = 128;
     }
   }
-  ABCGPT_CHECK_ARG(bn == 128 || bn == 256 || bn == 512, "gemm: unsupported tile hint %d", bn);
-  const bool pair = bn == 512;
+  ABCGPT_CHECK_ARG(bn == 128 || bn == 256 || bn == 512 || bn == 1024, "gemm: unsupported tile hint %d", bn);
+  const bool pair = bn >= 512;
+  // clusters of two CTA pairs sharing their B operand by TMA multicast (bn_hint 1024): needs an even number of 256-row
+  // tiles.  Measured on B200 it is a wash against plain pairs (1.32-1.37 vs 1.34-1.37 PFLOP/s on the cfg3 shapes: the L2
+  // already merges the two pairs' requests, and at the ~1.2 GHz the power cap allows in GEMM loops the pair kernel runs at
+  // > 90 % of the tensor peak), so it is opt-in.
+  const bool quad = pair && bn_hint == 1024 && (((M + 255) / 256) % 2 == 0);
   const int tile_n = pair ? 256 : bn;
   const int num_n_blk = (N + tile_n - 1) / tile_n;
-  const int num_m_units = pair ? (num_m_blk + 1) / 2 : num_m_blk;  // schedulable row blocks
-  const int units = pair ? sms / 2 : sms;                           // schedulable CTAs / CTA pairs
+  const int num_m_units = quad ? ((num_m_blk + 1) / 2) / 2 : (pair ? (num_m_blk + 1) / 2 : num_m_blk);  // schedulable row blocks
+  const int units = quad ? sms / 4 : (pair ? sms / 2 : sms);        // schedulable CTAs / CTA pairs / clusters
 
   int splits = 1;
   if (epi == ABCGPT_EPI_F32_RED) {
@@ -730,7 +792,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
     rc = encode_tmap_2d(&tmA, a, 2, M, K, lda * 2, 64, BK, true);
   if (rc) return rc;
   if (!b_mn)
-    rc = encode_tmap_2d(&tmB, b, 2, K, N, ldb * 2, BK, pair ? 128 : bn, true);
+    rc = encode_tmap_2d(&tmB, b, 2, K, N, ldb * 2, BK, quad ? 64 : (pair ? 128 : bn), true);
   else
     rc = encode_tmap_2d(&tmB, b, 2, N, K, ldb * 2, 64, BK, true);
   if (rc) return rc;
@@ -750,10 +812,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   }
 
   const long long total = static_cast<long long>(num_m_units) * num_n_blk * splits;
-  if (pair) {
-    const int grid = 2 * static_cast<int>(total < units ? total : units);
-    return dispatch_major2(a_mn, b_mn, epi, tmA, tmB, p, grid, stream);
-  }
+  if (pair) return dispatch_major2(a_mn, b_mn, epi, tmA, tmB, p, total, quad, stream);
   const int grid = static_cast<int>(total < sms ? total : sms);
   if (bn == 256) return dispatch_major<256>(a_mn, b_mn, epi, tmA, tmB, p, grid, stream);
   return dispatch_major<128>(a_mn, b_mn, epi, tmA, tmB, p, grid, stream);

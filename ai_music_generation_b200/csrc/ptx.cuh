@@ -224,6 +224,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the tile lands at the same shared-memory offset in every CTA of cta_mask and the bytes are credited
+// to the barrier at the given offset in the pair leader of each destination CTA
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* tm, uint32_t mbar_cluster_addr, int c0,
+                                                   int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
                : "memory");
