@@ -10,7 +10,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ai_music_generation_b200 import ops  # noqa: E402
 
-which = set(sys.argv[1:]) or {"gemm", "attn", "ln", "adamw"}
+which = set(a for a in sys.argv[1:] if a != "once") or {"gemm", "attn", "ln", "adamw"}
+REP = 1 if "once" in sys.argv[1:] else 2  # "once": every kernel exactly one time (small ncu reports)
 dev = "cuda"
 torch.manual_seed(0)
 M, C, H, B, T = 32768, 768, 12, 32, 1024
@@ -18,7 +19,7 @@ if "gemm" in which:
     x = torch.randn(M, C, device=dev).bfloat16()
     w = torch.randn(3 * C, C, device=dev).bfloat16()
     out = torch.empty(M, 3 * C, device=dev, dtype=torch.bfloat16)
-    for _ in range(2):
+    for _ in range(REP):
         ops.gemm(x, w, epilogue=ops.EPI_BF16, out=out)                       # fwd NT, N=2304
     dy = torch.randn(M, 4 * C, device=dev).bfloat16()
     wfc = torch.randn(4 * C, C, device=dev).bfloat16()
@@ -37,7 +38,7 @@ if "attn" in which:
     do = torch.randn(B * T, C, device=dev).bfloat16()
     dqkv = torch.empty(B * T, 3 * C, device=dev, dtype=torch.bfloat16)
     delta = torch.empty(B, H, T, device=dev)
-    for _ in range(2):
+    for _ in range(REP):
         ops.attn_fwd(qkv, o, lse, B, T, H)
         ops.attn_bwd(qkv, o, do, lse, delta, dqkv, B, T, H)
 if "ln" in which:
@@ -50,7 +51,7 @@ if "ln" in which:
     dxo = torch.empty(M, C, device=dev)
     dxb = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
     dw = torch.zeros(C, device=dev)
-    for _ in range(2):
+    for _ in range(REP):
         ops.layernorm_fwd(x, w, None, y, st[0], st[1])
         ops.layernorm_bwd(dy, x, w, st[0], st[1], dres, dxo, dxb, dw, None)
 if "adamw" in which:
@@ -61,7 +62,7 @@ if "adamw" in which:
     v = torch.zeros(n, device=dev)
     sh = torch.empty(n, device=dev, dtype=torch.bfloat16)
     ss = torch.zeros(1, device=dev)
-    for _ in range(2):
+    for _ in range(REP):
         ops.sumsq(g, ss)
         ops.adamw(p, g, m, v, sh, lr=1e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.1, step=3, sumsq=ss, max_norm=1.0)
 torch.cuda.synchronize()
