@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libabcgpt.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "abcgpt.h")
 
 EPI_BF16, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_F32_RED, EPI_F32 = range(6)
+ACT_TANH = 0x100  # OR-ed into EPI_GELU / EPI_DGELU: tanh form of GELU (include/abcgpt.h ABCGPT_ACT_TANH)
 
 _P = c_void_p
 _SIGNATURES = {

@@ -39,6 +39,7 @@ struct GemmParams {
   const void* aux;
   long long ldaux;
   const float* bias;
+  int act_tanh;  // GELU / DGELU epilogues: 0 = exact erf (nn.GELU()), 1 = tanh form (HF "gelu_new", TunesFormer's GPT-2 blocks)
   int wide;  // 1: every epilogue pointer / leading dimension is 32-byte aligned -> 256-bit global accesses
   DropCfg drop;  // RESID epilogue only: dropout on the Linear output before the residual add (model.py:75-76,91)
   unsigned long long* stats;  // optional debug counters (cycles): [0] producer empty-wait, [1] mma full-wait,
@@ -96,6 +97,32 @@ __device__ __forceinline__ float2 gelu_bwd2(float2 x) {
   // pdf = exp(-x^2/2) / sqrt(2 pi)
   const float2 pdf = __fmul2_rn(e, make_float2(0.39894228040143268f, 0.39894228040143268f));
   return __ffma2_rn(x, pdf, cdf);
+}
+
+// tanh form: gelu_new(x) = 0.5 x (1 + tanh(k (x + 0.044715 x^3))), k = sqrt(2/pi)   (tunesformer/utils.py: HF GPT2 activation)
+__device__ __forceinline__ float2 gelu_tanh_t2(float2 x, float2& inner_deriv) {
+  const float2 xx = __fmul2_rn(x, x);
+  const float2 u = __fmul2_rn(x, __ffma2_rn(xx, make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f)));
+  inner_deriv = __ffma2_rn(xx, make_float2(0.1070322243f, 0.1070322243f), make_float2(0.7978845608f, 0.7978845608f));
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  return t;
+}
+__device__ __forceinline__ float2 gelu_tanh_fwd2(float2 x) {
+  float2 du;
+  const float2 t = gelu_tanh_t2(x, du);
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
+__device__ __forceinline__ float2 gelu_tanh_bwd2(float2 x) {
+  float2 du;
+  const float2 t = gelu_tanh_t2(x, du);
+  // 0.5 (1 + t) + 0.5 x (1 - t^2) du
+  const float2 omt2 = __ffma2_rn(t, make_float2(-t.x, -t.y), make_float2(1.0f, 1.0f));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  const float2 a = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  return __ffma2_rn(__fmul2_rn(hx, omt2), du, a);
 }
 
 // ---- epilogues: one thread owns 32 consecutive columns of one output row -------------------------------
@@ -165,8 +192,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
       for (int i = 0; i < 16; ++i) {
         const uint32_t hw = aux.v[i >> 3].v[i & 7];
         const uint32_t db = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        const float2 d = __fmul2_rn(make_float2(ptx::bf16lo(db), ptx::bf16hi(db)),
-                                    gelu_bwd2(make_float2(ptx::bf16lo(hw), ptx::bf16hi(hw))));
+        const float2 hx = make_float2(ptx::bf16lo(hw), ptx::bf16hi(hw));
+        const float2 d = __fmul2_rn(make_float2(ptx::bf16lo(db), ptx::bf16hi(db)), p.act_tanh ? gelu_tanh_bwd2(hx) : gelu_bwd2(hx));
         pk[i] = ptx::pack_bf16x2(d.x, d.y);
       }
     } else {
@@ -180,7 +207,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
       uint32_t gk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float2 a = gelu_fwd2(make_float2(ptx::bf16lo(pk[i]), ptx::bf16hi(pk[i])));  // GELU of the bf16 h
+        const float2 hx = make_float2(ptx::bf16lo(pk[i]), ptx::bf16hi(pk[i]));  // GELU of the bf16 h
+        const float2 a = p.act_tanh ? gelu_tanh_fwd2(hx) : gelu_fwd2(hx);
         gk[i] = ptx::pack_bf16x2(a.x, a.y);
       }
 #pragma unroll
@@ -725,6 +753,9 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
               int epi, void* c, long long ldc, void* c2, long long ldc2, const void* aux, long long ldaux,
               const float* bias, int bn_hint, int splits_hint, float drop_p, uint32_t drop_key, cudaStream_t stream) {
 
+  const int act_tanh = (epi & ABCGPT_ACT_TANH) ? 1 : 0;
+  epi &= ~ABCGPT_ACT_TANH;
+  ABCGPT_CHECK_ARG(!act_tanh || epi == ABCGPT_EPI_GELU || epi == ABCGPT_EPI_DGELU, "gemm: ABCGPT_ACT_TANH only modifies the GELU / DGELU epilogues");
   ABCGPT_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M,N,K must be positive (got %d,%d,%d)", M, N, K);
   ABCGPT_CHECK_ARG(N % 8 == 0, "gemm: N must be a multiple of 8 (pad the output; got %d)", N);
   ABCGPT_CHECK_ARG(c != nullptr, "gemm: null output");
@@ -801,7 +832,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   p.M = M; p.N = N; p.K = K;
   p.num_m_blk = num_m_blk; p.num_n_blk = num_n_blk; p.num_k_blk = num_k_blk;
   p.splits = splits; p.kb_per_split = kb_per_split;
-  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.stats = g_gemm_stats; p.drop = make_drop(drop_p, drop_key);
+  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.act_tanh = act_tanh; p.stats = g_gemm_stats; p.drop = make_drop(drop_p, drop_key);
   {
     const bool f32_out = (epi == ABCGPT_EPI_RESID || epi == ABCGPT_EPI_F32 || epi == ABCGPT_EPI_F32_RED);
     const long long cb = f32_out ? 4 : 2, ab = (epi == ABCGPT_EPI_RESID) ? 4 : 2;

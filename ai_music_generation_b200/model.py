@@ -39,6 +39,9 @@ class GPTConfig:
     n_embd: int = 768
     dropout: float = 0.0
     bias: bool = True
+    # not in the reference's GPTConfig (model.py:108-116): "gelu" = nn.GELU() exact erf (the reference, default);
+    # "gelu_tanh" = HF "gelu_new", the activation of the GPT-2 blocks TunesFormer is built from (tunesformer/utils.py:84-154)
+    activation: str = "gelu"
 
 
 # The sub-modules below only own parameters (names / shapes / init identical to the reference); the arithmetic of
@@ -173,6 +176,8 @@ class GPT(nn.Module):
         super().__init__()
         assert config.vocab_size is not None and config.block_size is not None
         assert config.n_embd // config.n_head == 64, "the sm_100a attention kernels are specialised for head size 64"
+        assert config.activation in ("gelu", "gelu_tanh"), config.activation
+        self._act = ops.ACT_TANH if config.activation == "gelu_tanh" else 0
         self.config = config
         self.transformer = nn.ModuleDict(dict(
             wte=nn.Embedding(config.vocab_size, config.n_embd),
@@ -347,7 +352,7 @@ class GPT(nn.Module):
             ops.gemm(bufs.att[k], lw["attn.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=bufs.xmid[k], aux=x_in,
                      bias=b("attn.c_proj.bias"), drop_p=p_drop, drop_key=keys[2 + 3 * li])
             ops.layernorm_fwd(bufs.xmid[k], lw["ln_2.weight"][0], b("ln_2.bias"), bufs.ln2[k], st[2], st[3])
-            ops.gemm(bufs.ln2[k], lw["mlp.c_fc.weight"][1], epilogue=ops.EPI_GELU, out=bufs.h[k], out2=bufs.g[k],
+            ops.gemm(bufs.ln2[k], lw["mlp.c_fc.weight"][1], epilogue=ops.EPI_GELU | self._act, out=bufs.h[k], out2=bufs.g[k],
                      bias=b("mlp.c_fc.bias"))
             ops.gemm(bufs.g[k], lw["mlp.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=x_out, aux=bufs.xmid[k],
                      bias=b("mlp.c_proj.bias"), drop_p=p_drop, drop_key=keys[3 + 3 * li])
@@ -408,7 +413,7 @@ class GPT(nn.Module):
             ops.gemm(bufs.dxb, bufs.g[li], a_mn=True, b_mn=True, epilogue=ops.EPI_F32_RED, out=lw["mlp.c_proj.weight"][2])
             if lw["mlp.c_proj.bias"] is not None:
                 ops.colsum_bf16(bufs.dxb, lw["mlp.c_proj.bias"][2])
-            ops.gemm(bufs.dxb, lw["mlp.c_proj.weight"][1], b_mn=True, epilogue=ops.EPI_DGELU, out=bufs.dh, aux=bufs.h[li])
+            ops.gemm(bufs.dxb, lw["mlp.c_proj.weight"][1], b_mn=True, epilogue=ops.EPI_DGELU | self._act, out=bufs.dh, aux=bufs.h[li])
             ops.gemm(bufs.dh, bufs.ln2[li], a_mn=True, b_mn=True, epilogue=ops.EPI_F32_RED, out=lw["mlp.c_fc.weight"][2])
             if lw["mlp.c_fc.bias"] is not None:
                 ops.colsum_bf16(bufs.dh, lw["mlp.c_fc.bias"][2])
@@ -548,7 +553,7 @@ class GPT(nn.Module):
             ops.gemm(st.att, lw["attn.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=y, aux=x, bias=b("attn.c_proj.bias"),
                      tile_n=128)
             ops.layernorm_fwd(y, lw["ln_2.weight"][0], b("ln_2.bias"), st.ln, st.stat[0], st.stat[1])
-            ops.gemm(st.ln, lw["mlp.c_fc.weight"][1], epilogue=ops.EPI_GELU, out=st.h, out2=st.g, bias=b("mlp.c_fc.bias"),
+            ops.gemm(st.ln, lw["mlp.c_fc.weight"][1], epilogue=ops.EPI_GELU | self._act, out=st.h, out2=st.g, bias=b("mlp.c_fc.bias"),
                      tile_n=128)
             ops.gemm(st.g, lw["mlp.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=x, aux=y, bias=b("mlp.c_proj.bias"),
                      tile_n=128)

@@ -42,6 +42,7 @@ class OracleConfig:
     n_embd: int = 768
     dropout: float = 0.0
     bias: bool = False
+    activation: str = "gelu"  # "gelu" = nn.GELU() exact erf (nanoGPT/model.py:83); "gelu_tanh" = HF gelu_new (tunesformer/utils.py GPT-2 blocks)
 
 
 def param_names(cfg: OracleConfig) -> list[str]:
@@ -145,7 +146,7 @@ def _drop(x, mask, p, bf16):
     return _bf(y) if bf16 else y
 
 
-def _attention(qkv, n_head, bf16, drop_mask=None, p=0.0):
+def _attention(qkv, n_head, bf16, drop_mask=None, p=0.0, key_padding=None):
     B, T, C3 = qkv.shape
     C = C3 // 3
     hs = C // n_head
@@ -153,12 +154,14 @@ def _attention(qkv, n_head, bf16, drop_mask=None, p=0.0):
     q = q.view(B, T, n_head, hs).transpose(1, 2)
     k = k.view(B, T, n_head, hs).transpose(1, 2)
     v = v.view(B, T, n_head, hs).transpose(1, 2)
-    if not bf16 and drop_mask is None:  # same call the reference makes (model.py:64); the explicit form below is its definition (:67-71)
+    if not bf16 and drop_mask is None and key_padding is None:  # same call the reference makes (model.py:64); the explicit form below is its definition (:67-71)
         y = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=True)
         return y.transpose(1, 2).contiguous().view(B, T, C)
     att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(hs))
     mask = torch.ones(T, T, dtype=torch.bool).tril()
     att = att.masked_fill(~mask, float("-inf"))
+    if key_padding is not None:  # HF attention_mask of TunesFormer's char decoder (tunesformer/utils.py:128-133,152-154): bool [B, T], True = pad key
+        att = att.masked_fill(key_padding[:, None, None, :] & ~torch.eye(T, dtype=torch.bool)[None, None], float("-inf"))
     att = torch.softmax(att, dim=-1)
     if drop_mask is not None:  # attn_dropout (:70) / SDPA dropout_p (:64) on the probabilities
         att = att * drop_mask.to(att.dtype) / (1.0 - p)
@@ -169,7 +172,8 @@ def _attention(qkv, n_head, bf16, drop_mask=None, p=0.0):
     return _bf(y) if bf16 else y
 
 
-def forward(sd, cfg: OracleConfig, idx, targets=None, bf16: bool = False, return_hidden: bool = False, masks=None):
+def forward(sd, cfg: OracleConfig, idx, targets=None, bf16: bool = False, return_hidden: bool = False, masks=None,
+            key_padding=None):
     """(logits, loss) exactly as GPT.forward: full logits with targets, last position only without.
 
     masks (training with dropout): {'p': float, 'emb': bool [B,T,C], 'attn_p': [L x bool [B,H,T,T]],
@@ -185,11 +189,11 @@ def forward(sd, cfg: OracleConfig, idx, targets=None, bf16: bool = False, return
         p = f"transformer.h.{i}."
         h = _layer_norm(x, sd[p + "ln_1.weight"], g(p + "ln_1.bias"))
         qkv = _linear(h, sd[p + "attn.c_attn.weight"], g(p + "attn.c_attn.bias"), bf16)
-        a = _attention(qkv, cfg.n_head, bf16, mk("attn_p", i), pd)
+        a = _attention(qkv, cfg.n_head, bf16, mk("attn_p", i), pd, key_padding)
         x = x + _drop(_linear(a, sd[p + "attn.c_proj.weight"], g(p + "attn.c_proj.bias"), bf16), mk("attn_resid", i), pd, bf16)
         h = _layer_norm(x, sd[p + "ln_2.weight"], g(p + "ln_2.bias"))
         h = _linear(h, sd[p + "mlp.c_fc.weight"], g(p + "mlp.c_fc.bias"), bf16)
-        h = F.gelu(h)
+        h = F.gelu(h, approximate="tanh") if cfg.activation == "gelu_tanh" else F.gelu(h)
         if bf16:
             h = _bf(h)
         x = x + _drop(_linear(h, sd[p + "mlp.c_proj.weight"], g(p + "mlp.c_proj.bias"), bf16), mk("mlp_resid", i), pd, bf16)

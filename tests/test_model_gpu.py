@@ -240,3 +240,47 @@ def test_generate_kv_cache_equals_context_recompute_and_slides_like_reference(cu
     torch.manual_seed(0)
     c = model.generate(prompt.to(cuda_device), 10, temperature=0.8, top_k=5)
     assert c.shape == (3, 16) and int(c.max()) < cfg.vocab_size and int(c.min()) >= 0
+
+
+def test_tunesformer_char_decoder_shape_matches_bf16_oracle(cuda_device):
+    """BASELINE config 4: the char-level decoder of TunesFormer is a GPT-2 stack with biases, the tanh
+    GELU ("gelu_new"), T = 32 characters per bar patch, V = 128, right-padded patches whose pad positions carry no loss
+    (tunesformer/utils.py:108-154: labels -100 at pads, attention_mask = non-pad).  With causal attention and RIGHT padding
+    a valid query never sees a pad key, so the key-padding mask only changes rows whose targets are ignored: the shape runs
+    through the same kernels with `activation="gelu_tanh"`, `bias=True` and ignore_index targets.  Compared with the
+    oracle's fp32 truth and its bf16-autocast emulation exactly like the nanoGPT configs above."""
+    cfg_dict = dict(block_size=32, vocab_size=128, n_layer=3, n_head=2, n_embd=128, dropout=0.0, bias=True,
+                    activation="gelu_tanh")
+    cfg = O.OracleConfig(**cfg_dict)
+    sd = O.synthetic_state(cfg, seed=3)
+    B, T = 96, 32   # 96 bar patches
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(3, 128, (B, T), generator=g)
+    lens = torch.randint(8, 33, (B,), generator=g)          # characters per patch ~ U[8, 32], tail padded with 0
+    pad = torch.arange(T)[None, :] >= lens[:, None]
+    x[pad] = 0
+    y = torch.roll(x, -1, dims=1)
+    y[:, -1] = 0
+    y[torch.roll(pad, -1, dims=1) | pad] = -1                 # no loss where the target (or the input) is padding
+    y[:, -1] = -1
+    model = make_model(cfg_dict, sd, cuda_device).train()
+    logits, loss = model(x.to(cuda_device), y.to(cuda_device))
+    loss.backward()
+    torch.set_num_threads(8)
+    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd, cfg, x, y, bf16=True)
+    tru_loss, tru_logits, tru_grads = O.loss_and_grads(sd, cfg, x, y, bf16=False)
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3
+    valid = ~pad
+    ours = (logits.float().cpu() - tru_logits).abs()[valid]
+    refs = (ref_logits - tru_logits).abs()[valid]
+    assert ours.max().item() <= 1.5 * refs.max().item() + 1e-2
+    assert ours.mean().item() <= 1.5 * refs.mean().item() + 1e-3
+    named = dict(model.named_parameters())
+    for n, tg in tru_grads.items():
+        got = named[n].grad.float().cpu()
+        ours_rel = ((got - tg).norm() / tg.norm()).item()
+        ref_rel = ((ref_grads[n] - tg).norm() / tg.norm()).item()
+        assert ours_rel <= 1.5 * ref_rel + 5e-3, (n, ours_rel, ref_rel)
+    # the key-padding mask is a no-op for valid rows: masking pad keys explicitly in the oracle changes no valid logit
+    masked_logits = O.forward(sd, cfg, x, y, bf16=False, key_padding=pad)[0]
+    assert (masked_logits - tru_logits).abs()[valid].max().item() <= 1e-5

@@ -60,9 +60,11 @@ def _mismatch_map(got, ref, tol, rb=8, cb=16, max_r=128, max_c=128):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def case_gemm(name, M, N, K, a_mn, b_mn, epi, tile_n, splits=0, timing=True):
+def case_gemm(name, M, N, K, a_mn, b_mn, epi, tile_n, splits=0, timing=True, tanh=False):
     import torch
     from ai_music_generation_b200 import ops
+    approx = "tanh" if tanh else "none"   # tanh: HF gelu_new (ABCGPT_ACT_TANH)
+    act = ops.ACT_TANH if tanh else 0
     torch.manual_seed(0)
     dev = "cuda"
     A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
@@ -80,8 +82,8 @@ def case_gemm(name, M, N, K, a_mn, b_mn, epi, tile_n, splits=0, timing=True):
         out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
         out2 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
         h = acc.bfloat16()
-        ref2 = torch.nn.functional.gelu(h.float())
-        run = lambda: ops.gemm(a_arg, b_arg, a_mn=a_mn, b_mn=b_mn, epilogue=epi, out=out, out2=out2, tile_n=tile_n)
+        ref2 = torch.nn.functional.gelu(h.float(), approximate=approx)
+        run = lambda: ops.gemm(a_arg, b_arg, a_mn=a_mn, b_mn=b_mn, epilogue=epi | act, out=out, out2=out2, tile_n=tile_n)
         outs = [(out, acc, 0.02), (out2, ref2, 0.02)]
     elif epi == ops.EPI_RESID:
         resid = torch.randn(M, N, device=dev)
@@ -93,9 +95,9 @@ def case_gemm(name, M, N, K, a_mn, b_mn, epi, tile_n, splits=0, timing=True):
         hpre = torch.randn(M, N, device=dev).bfloat16()
         out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
         hf = hpre.float().requires_grad_(True)
-        torch.nn.functional.gelu(hf).backward(acc.bfloat16().float())
+        torch.nn.functional.gelu(hf, approximate=approx).backward(acc.bfloat16().float())
         ref = hf.grad
-        run = lambda: ops.gemm(a_arg, b_arg, a_mn=a_mn, b_mn=b_mn, epilogue=epi, out=out, aux=hpre, tile_n=tile_n)
+        run = lambda: ops.gemm(a_arg, b_arg, a_mn=a_mn, b_mn=b_mn, epilogue=epi | act, out=out, aux=hpre, tile_n=tile_n)
         outs = [(out, ref, 0.02)]
     elif epi == ops.EPI_F32_RED:
         out = torch.zeros(M, N, device=dev)
@@ -346,6 +348,8 @@ def build_cases():
     cases["gemm2_ragged"] = lambda: case_gemm("gemm2_ragged", 328, 200, 136, False, False, E.EPI_BF16, 512, timing=False)
     cases["gemm2_gelu"] = lambda: case_gemm("gemm2_gelu", 1024, 1536, 384, False, False, E.EPI_GELU, 512, timing=False)
     cases["gemm2_resid"] = lambda: case_gemm("gemm2_resid", 1024, 384, 1536, False, False, E.EPI_RESID, 512, timing=False)
+    cases["gemm2_gelu_tanh"] = lambda: case_gemm("gemm2_gelu_tanh", 1024, 1536, 384, False, False, E.EPI_GELU, 512, timing=False, tanh=True)
+    cases["gemm2_dgelu_tanh"] = lambda: case_gemm("gemm2_dgelu_tanh", 1024, 1536, 384, False, True, E.EPI_DGELU, 512, timing=False, tanh=True)
     cases["gemm2_dgelu"] = lambda: case_gemm("gemm2_dgelu", 1024, 1536, 384, False, True, E.EPI_DGELU, 512, timing=False)
     cases["gemm_nt_ragged"] = lambda: case_gemm("gemm_nt_ragged", 200, 96, 136, False, False, E.EPI_BF16, 128, timing=False)
     cases["gemm_nt_f32"] = lambda: case_gemm("gemm_nt_f32", 256, 256, 768, False, False, E.EPI_F32, 256, timing=False)
