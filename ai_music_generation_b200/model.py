@@ -583,14 +583,18 @@ class GPT(nn.Module):
             out_col[:, 0].copy_(nxt)
 
     @torch.no_grad()
-    def generate(self, idx, max_new_tokens, temperature=1.0, top_k=None, use_cache=True):
+    def generate(self, idx, max_new_tokens, temperature=1.0, top_k=None, use_cache=True, stop_token=None, stop_check_every=64):
         """Reference semantics (model.py:305-330): feed the sequence back max_new_tokens times, last-position logits,
         temperature, optional top-k, sample, append; the context is cropped to block_size.
 
         While the context window does not slide (position < block_size) each new token costs ONE single-position step over
         a KV cache instead of the reference's full-context forward; absolute position embeddings make the cache invalid
         once the window slides, so from there on the context is recomputed per token exactly like the reference.
-        top_k == 1 (greedy) uses the fused argmax head writing straight into the pre-allocated token buffer."""
+        top_k == 1 (greedy) uses the fused argmax head writing straight into the pre-allocated token buffer.
+
+        stop_token (extension, default off): sample.py cuts every generated tune at the first end-of-tune symbol
+        (sample.py:163-165), so once EVERY sequence of the batch has produced it the remaining steps cannot change the
+        written files; checked every `stop_check_every` tokens (one host sync each), the tail is filled with stop_token."""
         if not idx.is_cuda:
             raise _C.AbcgptError("GPT.generate: idx must be a CUDA tensor (there is no CPU path)")
         B, T0 = idx.shape
@@ -611,12 +615,21 @@ class GPT(nn.Module):
                 last = min(total - 1, bs)   # positions 0 .. last-1 can be decoded with the cache
                 st.col[:T0].copy_(idx.t())
                 greedy = top_k is not None and min(top_k, self.config.vocab_size) == 1
+                stopped = False
                 for t in range(last):
                     want = t >= T0 - 1
                     self._decode_step(st, t, want, greedy and want)
                     if want and not greedy:
                         self._sample(st.logits, st.col[t + 1], 1, temperature, top_k)
+                    if stop_token is not None and t >= T0 and (t - T0) % stop_check_every == stop_check_every - 1:
+                        if bool((st.col[T0:t + 2] == stop_token).any(dim=0).all()):
+                            st.col[t + 2:last + 1].fill_(stop_token)
+                            stopped = True
+                            break
                 out[:, :last + 1].copy_(st.col[:last + 1].t())
+                if stopped:
+                    out[:, last + 1:].fill_(stop_token)
+                    return out
                 t = last
             for pos in range(max(t, T0 - 1), total - 1):  # window slides (or cache disabled): reference-style recompute
                 lo = max(0, pos + 1 - bs)

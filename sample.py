@@ -23,7 +23,9 @@ from configurator import load_settings
 DEFAULTS = dict(
     dataset="music21_bach", use_validation_prefixes=True, tokens_format="midi", validation_path="",
     n_conditional_measures=4, out_dir="out", init_from="resume", start="$", num_samples=1000, max_new_tokens=500,
-    temperature=0.8, top_k=200, seed=1337, device="cuda", dtype="bfloat16", compile=False, batch=64,
+    temperature=0.8, top_k=200, seed=1337, device="cuda", dtype="bfloat16", compile=False,
+    batch=64,          # new knob: prompts of equal length are decoded together (the reference decodes one at a time)
+    early_stop=True,   # new knob: stop a batch once every tune has produced its end symbol '$' (files are cut there anyway)
 )
 
 
@@ -87,7 +89,9 @@ def main():
         raise SystemExit(f"{meta_path} not found (the GPT-2 BPE fallback of the reference needs tiktoken + network)")
     print(f"Loading meta from {meta_path}...")
     with open(meta_path, "rb") as f:
-        encode, decode = build_codec(pickle.load(f), s["tokens_format"])
+        meta = pickle.load(f)
+        encode, decode = build_codec(meta, s["tokens_format"])
+    stop = meta["stoi"].get("$") if s["early_stop"] else None
 
     abc = s["tokens_format"] == "char" and s["dataset"] == "irishman"
     out_dir = os.path.join(s["out_dir"], "samples")
@@ -102,7 +106,7 @@ def main():
             for i in range(0, len(group), s["batch"]):
                 chunk = group[i:i + s["batch"]]
                 x = torch.tensor([ids for _, _, ids in chunk], dtype=torch.long, device=s["device"])
-                y = model.generate(x, s["max_new_tokens"], temperature=s["temperature"], top_k=top_k).tolist()
+                y = model.generate(x, s["max_new_tokens"], temperature=s["temperature"], top_k=top_k, stop_token=stop).tolist()
                 for (key, text, _), ids in zip(chunk, y):
                     res = decode(ids)
                     print(f"\nPrefix: {text}\nGeneration: {res}\n" + "-" * 50)

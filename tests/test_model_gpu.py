@@ -284,3 +284,28 @@ def test_tunesformer_char_decoder_shape_matches_bf16_oracle(cuda_device):
     # the key-padding mask is a no-op for valid rows: masking pad keys explicitly in the oracle changes no valid logit
     masked_logits = O.forward(sd, cfg, x, y, bf16=False, key_padding=pad)[0]
     assert (masked_logits - tru_logits).abs()[valid].max().item() <= 1e-5
+
+
+def test_generate_early_stop_is_output_equivalent(cuda_device):
+    """generate(stop_token=s): every row equals the unrestricted generation up to and including its first s after the prompt
+    (sample.py:163-165 cuts the written tune there), whatever happens later."""
+    g = load("tiny")
+    cfg = O.OracleConfig(**g["spec"]["cfg"])
+    sd = O.synthetic_state(cfg, seed=1)
+    model = make_model(g["spec"]["cfg"], sd, cuda_device).eval()
+    torch.manual_seed(0)
+    prompt = torch.randint(cfg.vocab_size, (6, 3)).to(cuda_device)
+    n_new = cfg.block_size - 3
+    assert n_new >= 32
+    full = model.generate(prompt, n_new, temperature=1.0, top_k=1).cpu()
+    gen = full[:, 3:]
+    common = [t for t in range(cfg.vocab_size) if bool((gen[:, :16] == t).any(dim=1).all())]
+    if not common:
+        pytest.skip("no token occurs in every row's first 16 generated tokens for this fixture")
+    s = common[0]
+    early = model.generate(prompt, n_new, temperature=1.0, top_k=1, stop_token=s, stop_check_every=8).cpu()
+    assert early.shape == full.shape
+    for b in range(full.shape[0]):
+        first = 3 + int((gen[b] == s).nonzero()[0])
+        assert torch.equal(early[b, : first + 1], full[b, : first + 1])
+    assert bool((early[:, -1] == s).all())   # the batch stopped early and the tail was filled

@@ -36,6 +36,9 @@ DEFAULTS = dict(
     decay_lr=True, warmup_iters=2000, lr_decay_iters=600000, min_lr=6e-5, backend="nccl", device="cuda",
     dtype="bfloat16", compile=False,
     device_loader=True,  # new knob: keep train.bin / val.bin in HBM and gather batches with one kernel (same batches as the host loader)
+    sharded_eval=True,   # new knob: under DDP every rank evaluates eval_iters / world batches and the sums are all-reduced
+                         # (the reference evaluates 2 x eval_iters batches on rank 0 while the other ranks wait, train.py:290-291)
+    activation="gelu",   # new knob: "gelu_tanh" = HF gelu_new (TunesFormer-shaped decoders); the reference is exact-erf "gelu"
 )
 
 
@@ -97,7 +100,7 @@ def main():
         print(f"found vocab_size = {vocab} (inside {meta_path})")
 
     model_args = dict(n_layer=s["n_layer"], n_head=s["n_head"], n_embd=s["n_embd"], block_size=s["block_size"],
-                      bias=s["bias"], vocab_size=None, dropout=s["dropout"])
+                      bias=s["bias"], vocab_size=None, dropout=s["dropout"], activation=s["activation"])
     iter_num, best_val = 0, 1e9
     checkpoint = None
     if s["init_from"] == "scratch":
@@ -109,6 +112,7 @@ def main():
         checkpoint = torch.load(os.path.join(s["out_dir"], "ckpt.pt"), map_location="cpu")
         for k in ("n_layer", "n_head", "n_embd", "block_size", "bias", "vocab_size"):
             model_args[k] = checkpoint["model_args"][k]
+        model_args["activation"] = checkpoint["model_args"].get("activation", "gelu")
         model = GPT(GPTConfig(**model_args))
         sd = {k.removeprefix("_orig_mod."): v for k, v in checkpoint["model"].items()}
         model.load_state_dict(sd)
@@ -127,18 +131,26 @@ def main():
     if ddp:
         model = DDP(model, device_ids=[local_rank])
 
+    shard_eval = ddp and s["sharded_eval"]
+
     @torch.no_grad()
     def estimate_loss():
+        """Mean loss over eval_iters batches per split (train.py:231-244).  Losses accumulate on the device (one host sync per
+        split instead of one per batch); under DDP with sharded_eval every rank takes eval_iters / world of the batches."""
         out = {}
-        model.eval()
+        raw_model.eval()
+        n_local = -(-s["eval_iters"] // world) if shard_eval else s["eval_iters"]
         for split in ("train", "val"):
-            losses = torch.zeros(s["eval_iters"])
-            for k in range(s["eval_iters"]):
+            acc = torch.zeros(1, device=device)
+            for _ in range(n_local):
                 X, Y = stream.get(split)
-                _, loss = model(X, Y)
-                losses[k] = loss.item()
-            out[split] = losses.mean()
-        model.train()
+                _, loss = raw_model(X, Y)
+                acc += loss
+            if shard_eval:
+                dist.all_reduce(acc)
+                acc /= world
+            out[split] = (acc / n_local).cpu()[0]
+        raw_model.train()
         return out
 
     log_path = os.path.join(s["out_dir"], "losses.jsonl")
@@ -152,8 +164,9 @@ def main():
         lr = lr_at(iter_num, s) if s["decay_lr"] else s["learning_rate"]
         for group in optimizer.param_groups:
             group["lr"] = lr
-        if iter_num % s["eval_interval"] == 0 and master:
+        if iter_num % s["eval_interval"] == 0 and (master or shard_eval):
             losses = estimate_loss()
+        if iter_num % s["eval_interval"] == 0 and master:
             print(f"[{datetime.now().strftime('%H:%M:%S')}] step {iter_num}: train loss {losses['train']:.4f}, "
                   f"val loss {losses['val']:.4f}")
             with open(log_path, "a") as f:
