@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libabcgpt.so")
-SOURCES = ["common.cu", "gemm.cu", "attn.cu", "layernorm.cu", "elementwise.cu", "api.cu"]
+SOURCES = ["common.cu", "gemm.cu", "attn.cu", "layernorm.cu", "elementwise.cu", "microbench.cu", "api.cu"]
 HEADERS = ["common.h", "kernels.h", "ptx.cuh", "dropout.cuh", os.path.join("..", "..", "include", "abcgpt.h")]
 
 NVCC_FLAGS = [

@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "100", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          "50", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -158,7 +158,7 @@ def attn_flops(meta, bwd):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
@@ -321,7 +321,10 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05, all fwd/dgrad/wgrad launches of a step)",
                      "achieved": achieved_tf, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved_tf / pk["sustained"],
                      "peak_kind": f"{pk['source']} sustained cuBLAS bf16", "launches_per_step": gemm_calls,
-                     "avg_launch_ms": gemm_ms / gemm_calls, "flops_per_step": gemm_fl, "traffic": None},
+                     "avg_launch_ms": gemm_ms / gemm_calls, "flops_per_step": gemm_fl,
+                     # DRAM bytes per launch (read + write) from profiles/r1c_ncu_full_summary.md: mean of the captured
+                     # forward / dgrad / wgrad / residual instantiations at the cfg3 shapes
+                     "traffic": 220e6 if args.workload == "cfg3" else None},
         "kernel_breakdown": fam,
     }
     if not args.no_cpu_baseline:
