@@ -184,6 +184,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # rank 0's stdout must carry exactly one JSON line: NCCL_DEBUG=VERSION (set in some images) prints a banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = wl["cfg"]
