@@ -26,6 +26,10 @@ _SIGNATURES = {
                                  c_int64, _P, c_int64, _P, c_int, c_int, c_float, c_uint32, _P]),
     "abcgpt_embed_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_uint32, _P]),
     "abcgpt_embed_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_uint32, _P]),
+    "abcgpt_add_pos": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "abcgpt_set_first_pos": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "abcgpt_pos_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "abcgpt_onehot_bf16": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "abcgpt_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "abcgpt_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_uint32, _P]),
     "abcgpt_attn_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, c_uint32, _P]),

@@ -30,6 +30,20 @@ int abcgpt_embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dw
   return embed_bwd(idx, dx, dwte, dwpe, M, T, C, V, dropout_p, dropout_key, S(stream));
 }
 
+/* hierarchical (TunesFormer-shaped) decoders: embeddings supplied by another network, one-hot patch rows */
+int abcgpt_add_pos(const float* e, const float* wpe, float* x, int M, int T, int C, void* stream) {
+  return add_pos(e, wpe, x, M, T, C, S(stream));
+}
+int abcgpt_set_first_pos(const float* first, const float* wpe, float* x, int B, int T, int C, void* stream) {
+  return set_first_pos(first, wpe, x, B, T, C, S(stream));
+}
+int abcgpt_pos_bwd(const float* dx, float* dwpe, int M, int T, int C, void* stream) {
+  return pos_bwd(dx, dwpe, M, T, C, S(stream));
+}
+int abcgpt_onehot_bf16(const int64_t* tok, void* out, int M, int S_, int V, void* stream) {
+  return onehot_bf16(tok, out, M, S_, V, S(stream));
+}
+
 int abcgpt_layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* y_f32,
                          float* mean, float* rstd, int M, int C, void* stream) {
   return layernorm_fwd(x, weight, bias, y_bf16, y_f32, mean, rstd, M, C, S(stream));

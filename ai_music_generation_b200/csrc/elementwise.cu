@@ -439,6 +439,43 @@ inline int grid_for(long long work_items, int threads, int waves = 8) {
   return static_cast<int>(g);
 }
 
+
+// ---- hierarchical (TunesFormer-shaped) decoders: embeddings that come from another network ----------------------------
+// x[m,:] = e[m,:] + wpe[m % T,:]   (HF GPT2Model(inputs_embeds=...), tunesformer/utils.py:102-106)
+__global__ void add_pos_kernel(const float4* __restrict__ e, const float4* __restrict__ wpe, float4* __restrict__ x,
+                               long long total, int T, int C4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / C4;
+    const int c = static_cast<int>(i - m * C4);
+    const float4 a = __ldg(e + i);
+    const float4 b = __ldg(wpe + (m % T) * C4 + c);
+    x[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+// x[b,0,:] = first[b,:] + wpe[0,:]: the char-level decoder's first input embedding is the encoded patch
+// (tunesformer/utils.py:146-150)
+__global__ void set_first_pos_kernel(const float4* __restrict__ first, const float4* __restrict__ wpe, float4* __restrict__ x,
+                                     int B, int T, int C4) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(B) * C4) return;
+  const long long b = i / C4;
+  const int c = static_cast<int>(i - b * C4);
+  const float4 a = __ldg(first + i), p = __ldg(wpe + c);
+  x[b * T * C4 + c] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+}
+// one-hot rows for the patch embedding Linear(S * V -> C) (tunesformer/utils.py:102-104): out[m, s * V + tok[m,s]] = 1
+__global__ void onehot_bf16_kernel(const int64_t* __restrict__ tok, __nv_bfloat16* __restrict__ out, long long total, int S,
+                                   int V) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  long long t = __ldg(tok + i);
+  t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+  const long long m = i / S;
+  const int s = static_cast<int>(i - m * S);
+  out[(m * S + s) * V + t] = __float2bfloat16(1.0f);
+}
+
 }  // namespace
 
 int embed_fwd(const int64_t* idx, const float* wte, const float* wpe, float* x, int M, int T, int C, int V, float drop_p,
@@ -482,6 +519,35 @@ int embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int
   embed_bwd_wte_direct_kernel<<<grid_for(total, 256), 256, 0, stream>>>(idx, reinterpret_cast<const float4*>(dx), dwte,
                                                                         total, C4, V, drop);
   return launch_status("embed_bwd_wte_direct_kernel");
+}
+
+int add_pos(const float* e, const float* wpe, float* x, int M, int T, int C, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(e && wpe && x && M > 0 && T > 0 && C % 4 == 0, "add_pos: bad arguments");
+  const long long total = static_cast<long long>(M) * (C / 4);
+  add_pos_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(e), reinterpret_cast<const float4*>(wpe),
+                                                           reinterpret_cast<float4*>(x), total, T, C / 4);
+  return launch_status("add_pos_kernel");
+}
+int set_first_pos(const float* first, const float* wpe, float* x, int B, int T, int C, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(first && wpe && x && B > 0 && T > 0 && C % 4 == 0, "set_first_pos: bad arguments");
+  const long long total = static_cast<long long>(B) * (C / 4);
+  set_first_pos_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(first), reinterpret_cast<const float4*>(wpe), reinterpret_cast<float4*>(x), B, T, C / 4);
+  return launch_status("set_first_pos_kernel");
+}
+int pos_bwd(const float* dx, float* dwpe, int M, int T, int C, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(dx && dwpe && M > 0 && T > 0 && M % T == 0 && C % 4 == 0, "pos_bwd: bad arguments");
+  const long long n = static_cast<long long>(T) * (C / 4);
+  embed_bwd_wpe_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, stream>>>(
+      reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dwpe), M / T, T, C / 4, make_drop(0.f, 0));
+  return launch_status("embed_bwd_wpe_kernel");
+}
+int onehot_bf16(const int64_t* tok, void* out, int M, int S, int V, cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(tok && out && M > 0 && S > 0 && V > 0, "onehot_bf16: bad arguments");
+  const long long total = static_cast<long long>(M) * S;
+  ABCGPT_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(total) * V * 2, stream));
+  onehot_bf16_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(tok, reinterpret_cast<__nv_bfloat16*>(out), total, S, V);
+  return launch_status("onehot_bf16_kernel");
 }
 
 int ce_fwd(const void* logits, long long ldl, const int64_t* targets, float* row_loss, int M, int V,

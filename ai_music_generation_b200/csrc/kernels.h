@@ -16,6 +16,11 @@ int embed_fwd(const int64_t* idx, const float* wte, const float* wpe, float* x, 
 int embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int M, int T, int C, int V, float drop_p,
               uint32_t drop_key, cudaStream_t stream);
 
+int add_pos(const float* e, const float* wpe, float* x, int M, int T, int C, cudaStream_t stream);
+int set_first_pos(const float* first, const float* wpe, float* x, int B, int T, int C, cudaStream_t stream);
+int pos_bwd(const float* dx, float* dwpe, int M, int T, int C, cudaStream_t stream);
+int onehot_bf16(const int64_t* tok, void* out, int M, int S, int V, cudaStream_t stream);
+
 int layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* y_f32, float* mean,
                   float* rstd, int M, int C, cudaStream_t stream);
 int layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean, const float* rstd,

@@ -117,6 +117,7 @@ class _Buffers:
         self.idx = torch.empty(B, T, device=device, dtype=torch.int64)   # static copies of the inputs: recorded launch plans
         self.tgt = torch.empty(B, T, device=device, dtype=torch.int64)   # hold raw pointers
         self.gl = e(1, dt=f32)
+        self.hidden = None   # fp32 ln_f output, allocated on first use by the hierarchical (inputs_embeds) path
         self.plans = {}
         if keep_activations:
             self.dx = [e(M, C, dt=f32) for _ in range(2)]
@@ -169,6 +170,35 @@ class _GPTStep(torch.autograd.Function):
     def backward(ctx, _grad_logits, grad_loss):
         ctx.model._backward_plan(ctx.bufs, ctx.idx, ctx.targets, grad_loss, ctx.drop)
         return None, None, None, None
+
+
+class _GPTEmbedsStep(torch.autograd.Function):
+    """The same launch plans for a decoder whose input embeddings come from another network (hierarchical models,
+    SURVEY.md 8f N1).  mode 1: x_in = inputs_embeds [B,T,C]; mode 2: x_in = the replacement of the first position's
+    embedding [B,C] next to token ids.  Returns (loss, fp32 ln_f output); either may be unused."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, x_in, idx, targets, want_hidden, mode):
+        bufs = model._forward_plan(idx, targets, keep_activations=True, embeds=x_in if mode == 1 else None,
+                                   first=x_in if mode == 2 else None, want_hidden=want_hidden)
+        B, T, C = bufs.B, bufs.T, model.config.n_embd
+        idx_b = None
+        if mode == 2:  # the wte gradient must skip position 0 (its embedding was replaced): abcgpt_embed_bwd skips ids < 0
+            idx_b = idx.clone()
+            idx_b[:, 0] = -1
+        ctx.model, ctx.bufs, ctx.idx, ctx.targets, ctx.drop = model, bufs, idx_b, targets, bufs.drop
+        ctx.want_hidden, ctx.mode, ctx.shape = want_hidden, mode, (B, T, C)
+        loss = bufs.loss.view(()).clone() if targets is not None else torch.zeros((), device=x_in.device)
+        hidden = bufs.hidden.view(B, T, C).clone() if want_hidden else torch.zeros(0, device=x_in.device)
+        return loss, hidden
+
+    @staticmethod
+    def backward(ctx, grad_loss, grad_hidden):
+        B, T, C = ctx.shape
+        d_hidden = grad_hidden.reshape(B * T, C).float() if ctx.want_hidden and ctx.targets is None else None
+        dx = ctx.model._backward_plan(ctx.bufs, ctx.idx, ctx.targets, grad_loss, ctx.drop, d_hidden=d_hidden, mode=ctx.mode)
+        gx = dx.view(B, T, C).clone() if ctx.mode == 1 else dx.view(B, T, C)[:, 0, :].clone()
+        return None, None, gx, None, None, None, None
 
 
 class GPT(nn.Module):
@@ -301,7 +331,10 @@ class GPT(nn.Module):
             self._bufs[key] = _Buffers(self.config, B, T, self._arena["flat"].device, keep)
         return self._bufs[key]
 
-    def _forward_plan(self, idx, targets, keep_activations):
+    def _forward_plan(self, idx, targets, keep_activations, embeds=None, first=None, want_hidden=False):
+        """embeds (fp32 [B,T,C]): the decoder is fed embeddings from another network (HF inputs_embeds) instead of token ids;
+        first (fp32 [B,C]): token ids, but the first position's embedding is replaced (TunesFormer char decoder);
+        want_hidden: also keep the fp32 ln_f output in bufs.hidden (HF last_hidden_state)."""
         cfg = self.config
         # Dropout (model.py:39-40,85,129 + SDPA dropout_p :64): counter-based masks, one key per site, derived from a seed
         # drawn from torch's CPU generator for every forward (reproducible under torch.manual_seed); the backward plan
@@ -313,22 +346,24 @@ class GPT(nn.Module):
             keys = [site_key(seed, i) for i in range(1 + 3 * cfg.n_layer)]
         else:
             seed, keys = None, [0] * (1 + 3 * cfg.n_layer)
-        if not idx.is_cuda:
-            raise _C.AbcgptError("GPT.forward: idx must be a CUDA tensor (there is no CPU path)")
+        src = embeds if embeds is not None else idx
+        if not src.is_cuda:
+            raise _C.AbcgptError("GPT.forward: inputs must be CUDA tensors (there is no CPU path)")
         self._ensure_device_state()
         layers = self._layer_tensors()
         top = self._arena["top"]
-        B, T = idx.shape
+        B, T = src.shape[0], src.shape[1]
         assert T <= cfg.block_size, f"Cannot forward sequence of length {T}, block size is only {cfg.block_size}"
         bufs = self._act_buffers(B, T, keep_activations)
         C, H, V = cfg.n_embd, cfg.n_head, cfg.vocab_size
-        idx = idx.contiguous()
+        if idx is not None:
+            idx = idx.contiguous()
         bufs.drop = (p_drop, keys, seed)
         self.last_dropout_seed = seed
         # Launch-plan cache: with dropout off every argument of every launch is static (arena views, per-shape buffers,
         # the stream), so the plan is recorded once and replayed; inputs are staged into static buffers.
         plan_key = None
-        if p_drop == 0.0 and self._plan_cache_enabled:
+        if p_drop == 0.0 and self._plan_cache_enabled and embeds is None and first is None and not want_hidden:
             bufs.idx.copy_(idx)
             idx = bufs.idx
             if targets is not None:
@@ -340,7 +375,16 @@ class GPT(nn.Module):
                 ops.replay(plan)
                 return bufs
             ops.begin_record()
-        ops.embed_fwd(idx, top["wte"][0], top["wpe"][0], bufs.x[0], T, drop_p=p_drop, drop_key=keys[0])
+        if embeds is not None:
+            if p_drop != 0.0:
+                raise _C.AbcgptError("inputs_embeds path: embedding dropout is not implemented (use dropout=0)")
+            ops.add_pos(embeds.contiguous().view(B * T, C), top["wpe"][0], bufs.x[0], T)
+        else:
+            ops.embed_fwd(idx, top["wte"][0], top["wpe"][0], bufs.x[0], T, drop_p=p_drop, drop_key=keys[0])
+            if first is not None:
+                if p_drop != 0.0:
+                    raise _C.AbcgptError("first-embedding path: embedding dropout is not implemented (use dropout=0)")
+                ops.set_first_pos(first.contiguous(), top["wpe"][0], bufs.x[0], T)
         for li, lw in enumerate(layers):
             k = li if keep_activations else 0
             x_in, x_out = bufs.x[k], bufs.x[k + 1] if keep_activations else bufs.x[0]
@@ -358,9 +402,14 @@ class GPT(nn.Module):
                      bias=b("mlp.c_proj.bias"), drop_p=p_drop, drop_key=keys[3 + 3 * li])
         x_last = bufs.x[cfg.n_layer] if keep_activations else bufs.x[0]
         lnf_b = None if top["ln_f.bias"] is None else top["ln_f.bias"][0]
-        ops.layernorm_fwd(x_last, top["ln_f.weight"][0], lnf_b, bufs.lnf, bufs.statf[0], bufs.statf[1])
+        if want_hidden and bufs.hidden is None:
+            bufs.hidden = torch.empty(B * T, C, device=bufs.lnf.device, dtype=torch.float32)
+        ops.layernorm_fwd(x_last, top["ln_f.weight"][0], lnf_b, bufs.lnf, bufs.statf[0], bufs.statf[1],
+                          y_f32=bufs.hidden if want_hidden else None)
         wte_bf16 = top["wte"][1]
-        if targets is not None:
+        if want_hidden and targets is None:
+            pass  # a decoder without a head (TunesFormer's patch level): the caller reads bufs.hidden
+        elif targets is not None:
             ops.gemm(bufs.lnf, wte_bf16, N=bufs.Vpad, epilogue=ops.EPI_BF16, out=bufs.logits)
             ops.ce_fwd(bufs.logits, targets.contiguous().view(-1), bufs.row_loss, bufs.sum_count, bufs.loss, V)
         else:  # last position only (model.py:190): strided A operand, no gather copy
@@ -370,7 +419,11 @@ class GPT(nn.Module):
             bufs.plans[plan_key] = ops.end_record()
         return bufs
 
-    def _backward_plan(self, bufs, idx, targets, grad_loss, drop):
+    def _backward_plan(self, bufs, idx, targets, grad_loss, drop, d_hidden=None, mode=0):
+        """mode 0: token ids in (the reference path); 1: inputs_embeds in (returns the fp32 gradient w.r.t. x[0], which is the
+        gradient of the embeddings); 2: token ids with a replaced first embedding (`idx` must carry -1 at position 0 so that
+        the wte gradient skips it; returns the same buffer, row 0 of every sequence is the gradient of `first`).
+        d_hidden (fp32 [M,C]): gradient of the ln_f output when the decoder has no head."""
         cfg = self.config
         p_drop, keys, _ = drop
         a = self._arena
@@ -383,23 +436,30 @@ class GPT(nn.Module):
             a["grad"].zero_()
             for p, o in zip(params, a["offs"]):
                 p.grad = a["grad"][o:o + p.numel()].view(p.shape)
-        bufs.gl.copy_(grad_loss.reshape(1))
+        if targets is not None:
+            bufs.gl.copy_(grad_loss.reshape(1))
         gl = bufs.gl
-        tflat = targets.contiguous().view(-1)
+        tflat = targets.contiguous().view(-1) if targets is not None else None
         sync = self._grad_sync if (self._grad_sync is not None and self.require_backward_grad_sync) else None
         plan_key = None
-        if p_drop == 0.0 and self._plan_cache_enabled and targets.data_ptr() == bufs.tgt.data_ptr():
+        if (p_drop == 0.0 and self._plan_cache_enabled and mode == 0 and d_hidden is None and targets is not None
+                and targets.data_ptr() == bufs.tgt.data_ptr()):
             plan_key = ("bwd", sync is not None, torch.cuda.current_stream().cuda_stream)
             plan = bufs.plans.get(plan_key)
             if plan is not None:
                 ops.replay(plan)
                 return
             ops.begin_record()
-        ops.ce_bwd(bufs.logits, tflat, bufs.sum_count, gl, bufs.dlogits, V)
         wte, wte_bf16, dwte = top["wte"]
-        # lm_head: dW[V,C] += dlogits^T lnf ; d(lnf) = dlogits W
-        ops.gemm(bufs.dlogits, bufs.lnf, a_mn=True, b_mn=True, M=V, N=C, K=M, epilogue=ops.EPI_F32_RED, out=dwte)
-        ops.gemm(bufs.dlogits, wte_bf16, b_mn=True, M=M, N=C, K=V, epilogue=ops.EPI_BF16, out=bufs.dln)
+        if targets is not None:
+            ops.ce_bwd(bufs.logits, tflat, bufs.sum_count, gl, bufs.dlogits, V)
+            # lm_head: dW[V,C] += dlogits^T lnf ; d(lnf) = dlogits W
+            ops.gemm(bufs.dlogits, bufs.lnf, a_mn=True, b_mn=True, M=V, N=C, K=M, epilogue=ops.EPI_F32_RED, out=dwte)
+            ops.gemm(bufs.dlogits, wte_bf16, b_mn=True, M=M, N=C, K=V, epilogue=ops.EPI_BF16, out=bufs.dln)
+            if d_hidden is not None:
+                raise _C.AbcgptError("backward: a loss head AND a hidden-state gradient on the same decoder is not implemented")
+        else:
+            ops.cast_bf16(d_hidden.contiguous().view(-1), bufs.dln.view(-1))
         dx, dx_other = bufs.dx[0], bufs.dx[1]
         gw = lambda t: None if t is None else t[2]  # noqa: E731
         # every bf16 stream gradient `dxb` is produced already masked for the residual-branch dropout of its consumer
@@ -438,11 +498,15 @@ class GPT(nn.Module):
             dx, dx_other = dx_other, dx
             if sync is not None:
                 ops.record_callback(lambda li=li: sync.layer_done(li))
-        ops.embed_bwd(idx.contiguous().view(-1), dx, dwte, top["wpe"][2], T, drop_p=p_drop, drop_key=keys[0])
+        if mode == 1:
+            ops.pos_bwd(dx, top["wpe"][2], T)
+        else:
+            ops.embed_bwd(idx.contiguous().view(-1), dx, dwte, top["wpe"][2], T, drop_p=p_drop, drop_key=keys[0])
         if sync is not None:
             ops.record_callback(sync.backward_done)
         if plan_key is not None:
             bufs.plans[plan_key] = ops.end_record()
+        return dx
 
     # ------------------------------------------------------------------------------------------------------
     # reference call surface
@@ -473,6 +537,25 @@ class GPT(nn.Module):
         if targets is not None:
             return bufs.logits.view(B, T, -1)[:, :, :V], bufs.loss.view(())
         return bufs.last_logits[:, :V].unsqueeze(1), None
+
+    def forward_hidden(self, inputs_embeds):
+        """HF `GPT2Model(inputs_embeds=...)`: position embeddings are added here, returns the fp32 ln_f output
+        (`last_hidden_state`), differentiable w.r.t. inputs_embeds (tunesformer/utils.py:96-106)."""
+        if not (torch.is_grad_enabled() and self._arena["params"][0].requires_grad):
+            with torch.no_grad():
+                bufs = self._forward_plan(None, None, keep_activations=False, embeds=inputs_embeds, want_hidden=True)
+            return bufs.hidden.view(*inputs_embeds.shape).clone()
+        anchor = self._anchor_tensor(inputs_embeds.device)
+        _, hidden = _GPTEmbedsStep.apply(anchor, self, inputs_embeds, None, None, True, 1)
+        return hidden
+
+    def forward_with_first(self, idx, first_embeds, targets):
+        """HF `GPT2LMHeadModel(inputs_embeds=cat(first, wte(idx)[:, 1:]), labels=...)`: token embeddings with the first
+        position replaced by `first_embeds` [B, C]; returns the loss over `targets` (already shifted by the caller,
+        ignore_index = -1), differentiable w.r.t. first_embeds (tunesformer/utils.py:120-154)."""
+        anchor = self._anchor_tensor(idx.device)
+        loss, _ = _GPTEmbedsStep.apply(anchor, self, first_embeds, idx, targets, False, 2)
+        return loss
 
     def _anchor_tensor(self, device):
         t = getattr(self, "_anchor", None)

@@ -127,6 +127,33 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_B
     return out
 
 
+def add_pos(e, wpe, x, T):
+    """x[m] = e[m] + wpe[m % T] (fp32): a decoder fed with embeddings from another network."""
+    _chk(e, torch.float32, "add_pos e")
+    M, C = x.shape
+    _call("add_pos", 1, (M, C), _C.lib().abcgpt_add_pos, e.data_ptr(), wpe.data_ptr(), x.data_ptr(), M, T, C, _stream())
+
+
+def set_first_pos(first, wpe, x, T):
+    """x[b, 0] = first[b] + wpe[0]: the encoded bar patch replaces the first character embedding."""
+    _chk(first, torch.float32, "set_first_pos first")
+    Bn, C = first.shape
+    _call("set_first_pos", 1, (Bn, C), _C.lib().abcgpt_set_first_pos, first.data_ptr(), wpe.data_ptr(), x.data_ptr(), Bn, T, C,
+          _stream())
+
+
+def pos_bwd(dx, dwpe, T):
+    M, C = dx.shape
+    _call("pos_bwd", 1, (M, C), _C.lib().abcgpt_pos_bwd, dx.data_ptr(), dwpe.data_ptr(), M, T, C, _stream())
+
+
+def onehot_bf16(tok, out, V):
+    """out[m, s * V + tok[m, s]] = 1 (bf16), everything else 0: the rows TunesFormer's patch embedding Linear sees."""
+    _chk(tok, torch.int64, "onehot tok")
+    M, S = tok.shape
+    _call("onehot", 1, (M, S, V), _C.lib().abcgpt_onehot_bf16, tok.data_ptr(), out.data_ptr(), M, S, V, _stream())
+
+
 def embed_fwd(idx, wte, wpe, x, T, drop_p=0.0, drop_key=0):
     _chk(idx, torch.int64, "embed idx")
     M = idx.numel()

@@ -173,15 +173,23 @@ def _attention(qkv, n_head, bf16, drop_mask=None, p=0.0, key_padding=None):
 
 
 def forward(sd, cfg: OracleConfig, idx, targets=None, bf16: bool = False, return_hidden: bool = False, masks=None,
-            key_padding=None):
+            key_padding=None, inputs_embeds=None, first_embeds=None):
     """(logits, loss) exactly as GPT.forward: full logits with targets, last position only without.
 
     masks (training with dropout): {'p': float, 'emb': bool [B,T,C], 'attn_p': [L x bool [B,H,T,T]],
     'attn_resid': [L x bool [B,T,C]], 'mlp_resid': [L x bool [B,T,C]]} — the keep-masks nn.Dropout would have drawn."""
-    B, T = idx.shape
+    # inputs_embeds [B,T,C]: HF GPT2Model(inputs_embeds=...) (tunesformer/utils.py:102-106); first_embeds [B,C]: the first
+    # position's token embedding is replaced (tunesformer/utils.py:146-150)
+    B, T = (inputs_embeds.shape[0], inputs_embeds.shape[1]) if inputs_embeds is not None else idx.shape
     assert T <= cfg.block_size
     g = (lambda n: sd.get(n))
-    x = sd["transformer.wte.weight"][idx] + sd["transformer.wpe.weight"][:T]
+    if inputs_embeds is not None:
+        tok = inputs_embeds
+    else:
+        tok = sd["transformer.wte.weight"][idx]
+        if first_embeds is not None:
+            tok = torch.cat((first_embeds.unsqueeze(1), tok[:, 1:, :]), dim=1)
+    x = tok + sd["transformer.wpe.weight"][:T]
     pd = masks["p"] if masks else 0.0
     mk = (lambda name, i=None: None if not masks else (masks[name] if i is None else masks[name][i]))
     x = _drop(x, mk("emb"), pd, False)

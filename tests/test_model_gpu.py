@@ -309,3 +309,76 @@ def test_generate_early_stop_is_output_equivalent(cuda_device):
         first = 3 + int((gen[b] == s).nonzero()[0])
         assert torch.equal(early[b, : first + 1], full[b, : first + 1])
     assert bool((early[:, -1] == s).all())   # the batch stopped early and the tail was filled
+
+
+def test_tunesformer_shaped_hierarchical_model_matches_bf16_oracle(cuda_device):
+    """BASELINE config 4 end to end: patch-level decoder (one-hot patch embedding GEMM, inputs_embeds stack,
+    hidden states out) feeding the first input embedding of the char-level decoder, HF-shifted loss that ignores pad
+    characters.  Loss and every gradient of BOTH decoders against the oracle (fp32 truth, bf16-autocast emulation), then one
+    clip + AdamW step on the two arenas."""
+    from ai_music_generation_b200 import GPTConfig, TunesFormerShaped
+    from oracle import tunesformer_oracle as TO
+    pc_d = dict(block_size=16, vocab_size=128, n_layer=2, n_head=2, n_embd=128, dropout=0.0, bias=True, activation="gelu_tanh")
+    cc_d = dict(block_size=32, vocab_size=128, n_layer=2, n_head=2, n_embd=128, dropout=0.0, bias=True, activation="gelu_tanh")
+    pc, cc = O.OracleConfig(**pc_d), O.OracleConfig(**cc_d)
+    psd, csd = O.synthetic_state(pc, seed=5), O.synthetic_state(cc, seed=6)
+    g = torch.Generator().manual_seed(0)
+    psd["patch_embedding.weight"] = torch.randn(128, 4096, generator=g) * 0.02
+    psd["patch_embedding.bias"] = torch.randn(128, generator=g) * 0.02
+    patches = torch.randint(3, 128, (6, 12, 32), generator=g)           # 6 tunes x 12 bar patches x 32 characters
+    lens = torch.randint(6, 33, (6, 12), generator=g)
+    patches[torch.arange(32)[None, None, :] >= lens[..., None]] = 0      # right-padded patches
+    model = TunesFormerShaped(GPTConfig(**pc_d), GPTConfig(**cc_d))
+    model.patch_level_decoder.load_state_dict({**psd, "lm_head.weight": psd["transformer.wte.weight"]})
+    model.char_level_decoder.load_state_dict({**csd, "lm_head.weight": csd["transformer.wte.weight"]})
+    model = model.to(cuda_device).train()
+    opt = model.configure_optimizers(0.1, 1e-3, (0.9, 0.95))
+    loss = model(patches.to(cuda_device))
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    torch.set_num_threads(8)
+    ref_loss, ref_pg, ref_cg = TO.loss_and_grads(psd, pc, csd, cc, patches, bf16=True)
+    tru_loss, tru_pg, tru_cg = TO.loss_and_grads(psd, pc, csd, cc, patches, bf16=False)
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3, (loss.item(), ref_loss.item(), tru_loss.item())
+    for dec, tru, ref in ((model.patch_level_decoder, tru_pg, ref_pg), (model.char_level_decoder, tru_cg, ref_cg)):
+        named = dict(dec.named_parameters())
+        for n, tg in tru.items():
+            if tg.norm().item() == 0.0:   # the patch level has no head: its (unused) wte receives no gradient
+                assert named[n].grad is None or named[n].grad.abs().max().item() == 0.0, n
+                continue
+            got = named[n].grad.float().cpu()
+            ours_rel = ((got - tg).norm() / tg.norm()).item()
+            ref_rel = ((ref[n] - tg).norm() / tg.norm()).item()
+            assert ours_rel <= 1.5 * ref_rel + 5e-3, (n, ours_rel, ref_rel)
+    total = model.clip_grad_norm_(1.0)
+    want = math.sqrt(O.grad_norm(tru_pg) ** 2 + O.grad_norm(tru_cg) ** 2)
+    assert total.item() == pytest.approx(want, rel=2e-2)
+    before = model.patch_level_decoder.patch_embedding.weight.detach().clone()
+    opt.step()
+    assert (model.patch_level_decoder.patch_embedding.weight.detach() - before).abs().max().item() > 0
+    loss2 = model(patches.to(cuda_device))
+    assert loss2.item() < loss.item()          # one AdamW step on the same batch lowers the loss
+
+
+def test_tunesformer_shaped_model_matches_reference_golden(cuda_device):
+    """The same hierarchical model against the numbers of the UNMODIFIED reference TunesFormer (fp32, CPU):
+    tests/golden/tunesformer_tiny.json, one tune of 12 bar patches, patch-level vocabulary of 1 like tunesformer/train.py:22-25."""
+    from ai_music_generation_b200 import GPTConfig, TunesFormerShaped
+    from oracle.make_golden_tunesformer import inputs
+    with open(os.path.join(GOLDEN, "tunesformer_tiny.json")) as f:
+        g = json.load(f)
+    pc, cc, psd, csd, patches = inputs(g["spec"])
+    model = TunesFormerShaped(GPTConfig(**g["spec"]["patch_cfg"]), GPTConfig(**g["spec"]["char_cfg"]))
+    model.patch_level_decoder.load_state_dict({**psd, "lm_head.weight": psd["transformer.wte.weight"]})
+    model.char_level_decoder.load_state_dict({**csd, "lm_head.weight": csd["transformer.wte.weight"]})
+    model = model.to(cuda_device).train()
+    loss = model(patches.to(cuda_device))
+    loss.backward()
+    assert abs(loss.item() - g["reference"]["loss"]) <= 5e-3
+    for dec, ref in ((model.patch_level_decoder, g["reference"]["patch_grad_norms"]),
+                     (model.char_level_decoder, g["reference"]["char_grad_norms"])):
+        named = dict(dec.named_parameters())
+        biggest = max(ref.values())
+        for n, v in ref.items():
+            got = 0.0 if named[n].grad is None else named[n].grad.norm().item()
+            assert abs(got - v) <= 0.05 * v + 2e-3 * biggest, (n, got, v)

@@ -98,3 +98,20 @@ def test_bf16_emulation_is_close_to_reference_autocast():
     _, loss = O.forward(sd, cfg, x, y, bf16=True)
     assert abs(loss.item() - g["steps"][0]["bf16_autocast_loss"]) < 5e-3
     assert math.isfinite(loss.item())
+
+
+def test_tunesformer_oracle_matches_reference_golden():
+    """oracle/tunesformer_oracle.py against the loss / gradient norms the unmodified reference TunesFormer produced
+    (oracle/make_golden_tunesformer.py)."""
+    import json
+    import os
+    from oracle import tunesformer_oracle as TO
+    from oracle.make_golden_tunesformer import inputs
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tunesformer_tiny.json")) as f:
+        g = json.load(f)
+    pc, cc, psd, csd, patches = inputs(g["spec"])
+    loss, pg, cg = TO.loss_and_grads(psd, pc, csd, cc, patches)
+    assert abs(loss.item() - g["reference"]["loss"]) <= 1e-6
+    for grads, ref in ((pg, g["reference"]["patch_grad_norms"]), (cg, g["reference"]["char_grad_norms"])):
+        for k, v in ref.items():
+            assert abs(grads[k].norm().item() - v) <= 1e-4 * max(v, 1e-3) + 1e-7, (k, grads[k].norm().item(), v)
