@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libabcgpt.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "abcgpt.h")
 
 EPI_BF16, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_F32_RED, EPI_F32 = range(6)
+FN_IDS = {"abcgpt_gemm_bf16": 1, "abcgpt_embed_fwd": 2, "abcgpt_layernorm_fwd": 3, "abcgpt_attn_decode": 4, "abcgpt_argmax": 5}
 ACT_TANH = 0x100  # OR-ed into EPI_GELU / EPI_DGELU: tanh form of GELU (include/abcgpt.h ABCGPT_ACT_TANH)
 
 _P = c_void_p
@@ -44,6 +45,7 @@ _SIGNATURES = {
     "abcgpt_attn_decode": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "abcgpt_sample_batch": (c_int, [_P, c_int, c_int64, _P, _P, _P, c_int, c_int, _P]),
     "abcgpt_colsum_bf16": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    "abcgpt_replay": (c_int, [_P, c_int64, c_int64]),
     "abcgpt_debug_gemm_stats": (c_int, [_P]),
     "abcgpt_debug_attn_trace": (c_int, [_P]),
     "abcgpt_debug_attn_cta_trace": (c_int, [_P]),

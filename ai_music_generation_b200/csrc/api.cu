@@ -2,6 +2,7 @@
 // types, no exceptions across the boundary.
 #include "common.h"
 #include "kernels.h"
+#include <string.h>
 
 using namespace abcgpt;
 namespace abcgpt { extern unsigned long long* g_gemm_stats; extern long long* g_attn_trace; extern long long* g_attn_cta_trace; int tmem_ld_bench(long long*, int, int, int, cudaStream_t); int mma_bench(long long*, int, int, int, cudaStream_t); int mma2_bench(long long*, int, int, cudaStream_t); }
@@ -101,6 +102,65 @@ int abcgpt_colsum_bf16(const void* dy, int64_t ld, int M, int N, float* out, voi
 int abcgpt_argmax(const void* logits, int64_t ldl, int V, int64_t* out, int64_t out_stride, int B, void* stream) {
   return argmax_rows(logits, ldl, V, out, out_stride, B, S(stream));
 }
+
+/*
+ * Replay of a recorded launch list with position-affine arguments (the decode loop of GPT.generate is launch-bound: ~90
+ * launches per generated token, ~10 us of Python / ctypes each).  prog: per call [function id, nargs, (value, delta) x nargs];
+ * every argument is passed as value + k * delta; pointers and integers as int64, floats as the bit pattern of a double.
+ */
+static inline float abcgpt_word_f(int64_t w) {
+  double d;
+  memcpy(&d, &w, sizeof(d));
+  return static_cast<float>(d);
+}
+#define P_(i) reinterpret_cast<void*>(a[i])
+#define CP_(T, i) reinterpret_cast<const T*>(a[i])
+#define MP_(T, i) reinterpret_cast<T*>(a[i])
+#define I_(i) static_cast<int>(a[i])
+int abcgpt_replay(const int64_t* prog, int64_t n_words, int64_t k) {
+  int64_t i = 0;
+  while (i < n_words) {
+    const int64_t fn = prog[i], nargs = prog[i + 1];
+    if (nargs < 0 || nargs > 24 || i + 2 + 2 * nargs > n_words) return fail(-1, "abcgpt_replay: malformed program at word %lld", (long long)i);
+    int64_t a[24];
+    for (int64_t j = 0; j < nargs; ++j) a[j] = prog[i + 2 + 2 * j] + k * prog[i + 3 + 2 * j];
+    i += 2 + 2 * nargs;
+    int rc = 0;
+    switch (fn) {
+      case ABCGPT_FN_GEMM:
+        if (nargs != 22) return fail(-1, "abcgpt_replay: gemm takes 22 arguments");
+        rc = abcgpt_gemm_bf16(P_(0), I_(1), a[2], P_(3), I_(4), a[5], I_(6), I_(7), I_(8), I_(9), P_(10), a[11], P_(12), a[13], P_(14),
+                              a[15], CP_(float, 16), I_(17), I_(18), abcgpt_word_f(a[19]), static_cast<uint32_t>(a[20]), P_(21));
+        break;
+      case ABCGPT_FN_EMBED_FWD:
+        if (nargs != 11) return fail(-1, "abcgpt_replay: embed_fwd takes 11 arguments");
+        rc = abcgpt_embed_fwd(CP_(int64_t, 0), CP_(float, 1), CP_(float, 2), MP_(float, 3), I_(4), I_(5), I_(6), I_(7),
+                              abcgpt_word_f(a[8]), static_cast<uint32_t>(a[9]), P_(10));
+        break;
+      case ABCGPT_FN_LAYERNORM_FWD:
+        if (nargs != 10) return fail(-1, "abcgpt_replay: layernorm_fwd takes 10 arguments");
+        rc = abcgpt_layernorm_fwd(CP_(float, 0), CP_(float, 1), CP_(float, 2), P_(3), MP_(float, 4), MP_(float, 5), MP_(float, 6), I_(7),
+                                  I_(8), P_(9));
+        break;
+      case ABCGPT_FN_ATTN_DECODE:
+        if (nargs != 7) return fail(-1, "abcgpt_replay: attn_decode takes 7 arguments");
+        rc = abcgpt_attn_decode(P_(0), P_(1), I_(2), I_(3), I_(4), I_(5), P_(6));
+        break;
+      case ABCGPT_FN_ARGMAX:
+        if (nargs != 7) return fail(-1, "abcgpt_replay: argmax takes 7 arguments");
+        rc = abcgpt_argmax(P_(0), a[1], I_(2), MP_(int64_t, 3), a[4], I_(5), P_(6));
+        break;
+      default:
+        return fail(-1, "abcgpt_replay: unknown function id %lld", (long long)fn);
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+#undef P_
+#undef CP_
+#undef MP_
+#undef I_
 
 /* debug: device pointer to 8 uint64 cycle counters filled by subsequent GEMM launches (NULL disables) */
 int abcgpt_debug_gemm_stats(void* device_counters) {

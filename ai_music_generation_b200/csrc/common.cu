@@ -1,5 +1,7 @@
 #include "common.h"
 
+#include <unordered_map>
+
 #include <mutex>
 
 namespace abcgpt {
@@ -42,8 +44,59 @@ static CUtensorMapDataType dtype_of(int elem_bytes) {
   return elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 }
 
+static int encode_tmap_2d_uncached(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                                   uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+
+// ---- descriptor cache ------------------------------------------------------------------------------------------------
+// A tensor map is a pure function of (pointer, element size, dims, pitch, box, swizzle) and costs a few microseconds of
+// driver time to encode.  The training step re-uses ~400 of them every iteration and the decode loop ~100 per generated
+// token (there the host-side launch cost IS the step time), so encoded maps are kept in a small per-thread table.
+namespace {
+struct TmapKey {
+  const void* ptr;
+  uint64_t inner, outer, row_bytes;
+  uint32_t box_inner, box_outer;
+  int elem_bytes, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && row_bytes == o.row_bytes && box_inner == o.box_inner &&
+           box_outer == o.box_outer && elem_bytes == o.elem_bytes && swizzle == o.swizzle;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.inner + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.outer * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+    h ^= (k.row_bytes + (static_cast<uint64_t>(k.box_inner) << 40) + (static_cast<uint64_t>(k.box_outer) << 20) +
+          (static_cast<uint64_t>(k.elem_bytes) << 4) + static_cast<uint64_t>(k.swizzle) + (h << 6) + (h >> 2));
+    return static_cast<size_t>(h);
+  }
+};
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>& tmap_cache() {
+  thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  return cache;
+}
+constexpr size_t kTmapCacheMax = 16384;
+}  // namespace
+
 int encode_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
                    uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+  const TmapKey key{ptr, inner, outer, row_bytes, box_inner, box_outer, elem_bytes, swizzle128 ? 1 : 0};
+  auto& cache = tmap_cache();
+  if (auto it = cache.find(key); it != cache.end()) {
+    *tm = it->second;
+    return 0;
+  }
+  const int rc = encode_tmap_2d_uncached(tm, ptr, elem_bytes, inner, outer, row_bytes, box_inner, box_outer, swizzle128);
+  if (rc == 0) {
+    if (cache.size() >= kTmapCacheMax) cache.clear();
+    cache.emplace(key, *tm);
+  }
+  return rc;
+}
+
+static int encode_tmap_2d_uncached(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                                   uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-1, "TMA base pointer must be 16-byte aligned");

@@ -344,7 +344,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
   extern __shared__ float prob[];  // [n_keys]
   __shared__ float q[64];
   __shared__ float red[4];
-  __shared__ float part[2][64];
+  __shared__ float part[4][64];
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const __nv_bfloat16* base = cache + static_cast<long long>(b) * Tmax * 3 * C;
@@ -379,14 +379,33 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
   if (lane == 0) red[warp] = sum;
   __syncthreads();
   const float inv = 1.0f / ((red[0] + red[1]) + (red[2] + red[3]));
-  // out[d] = sum_k p_k V[k][d]: the flash kernels round P to bf16 before the second matmul; mirror that
-  const int d = tid & 63, half = tid >> 6;
-  float acc = 0.f;
-  for (int k = half; k < n_keys; k += 2)
-    acc += ptx::bf16_round(prob[k] * inv) * __bfloat162float(base[static_cast<long long>(k) * 3 * C + 2 * C + h * 64 + d]);
-  part[half][d] = acc;
+  // out[d] = sum_k p_k V[k][d]: the flash kernels round P to bf16 before the second matmul; mirror that.  Each warp takes
+  // every fourth key, a lane two adjacent columns (one 128 B row segment per warp instruction), four keys in flight per warp.
+  const uint32_t* vbase = reinterpret_cast<const uint32_t*>(base + 2 * C + h * 64) + lane;
+  const long long vstride = 3ll * C / 2;  // row stride in 32-bit words
+  float a0 = 0.f, a1 = 0.f;
+  int k = warp;
+  for (; k + 12 < n_keys; k += 16) {
+    const uint32_t v0 = __ldg(vbase + k * vstride), v1 = __ldg(vbase + (k + 4) * vstride);
+    const uint32_t v2 = __ldg(vbase + (k + 8) * vstride), v3 = __ldg(vbase + (k + 12) * vstride);
+    const float p0 = ptx::bf16_round(prob[k] * inv), p1 = ptx::bf16_round(prob[k + 4] * inv);
+    const float p2 = ptx::bf16_round(prob[k + 8] * inv), p3 = ptx::bf16_round(prob[k + 12] * inv);
+    a0 += p0 * ptx::bf16lo(v0); a1 += p0 * ptx::bf16hi(v0);
+    a0 += p1 * ptx::bf16lo(v1); a1 += p1 * ptx::bf16hi(v1);
+    a0 += p2 * ptx::bf16lo(v2); a1 += p2 * ptx::bf16hi(v2);
+    a0 += p3 * ptx::bf16lo(v3); a1 += p3 * ptx::bf16hi(v3);
+  }
+  for (; k < n_keys; k += 4) {
+    const uint32_t v0 = __ldg(vbase + k * vstride);
+    const float p0 = ptx::bf16_round(prob[k] * inv);
+    a0 += p0 * ptx::bf16lo(v0); a1 += p0 * ptx::bf16hi(v0);
+  }
+  part[warp][2 * lane] = a0;
+  part[warp][2 * lane + 1] = a1;
   __syncthreads();
-  if (tid < 64) out[static_cast<long long>(b) * C + h * 64 + tid] = __float2bfloat16_rn(part[0][tid] + part[1][tid]);
+  if (tid < 64)
+    out[static_cast<long long>(b) * C + h * 64 + tid] =
+        __float2bfloat16_rn((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]));
 }
 
 

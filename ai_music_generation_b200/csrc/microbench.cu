@@ -177,11 +177,13 @@ int mma2_bench(long long* out, int iters, int n, cudaStream_t stream) {
   const int smem = 100 * 1024;
   static bool done = false;
   if (!done) {
+    ABCGPT_CUDA(cudaFuncSetAttribute(mma2_bench_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ABCGPT_CUDA(cudaFuncSetAttribute(mma2_bench_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ABCGPT_CUDA(cudaFuncSetAttribute(mma2_bench_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     done = true;
   }
-  if (n == 128) mma2_bench_kernel<128><<<2, 128, smem, stream>>>(out, iters);
+  if (n == 64) mma2_bench_kernel<64><<<2, 128, smem, stream>>>(out, iters);
+  else if (n == 128) mma2_bench_kernel<128><<<2, 128, smem, stream>>>(out, iters);
   else mma2_bench_kernel<256><<<2, 128, smem, stream>>>(out, iters);
   return launch_status("mma2_bench_kernel");
 }

@@ -150,6 +150,7 @@ class _DecodeState:
         self.logits = e(B, self.Vpad)
         self.col = torch.zeros(Tmax + 1, B, device=device, dtype=torch.int64)  # token column t = contiguous int64 [B]
         self.plans = {}
+        self.affine = {}   # (flags) -> (t0, recorded plan at t0, per-launch argument deltas per position)
 
 
 class _GPTStep(torch.autograd.Function):
@@ -613,10 +614,21 @@ class GPT(nn.Module):
         """Position t of every sequence (tokens st.col[t]).  Appends this position's q|k|v to the cache and, if
         want_logits, leaves the next-token logits in st.logits (greedy: also writes the argmax into st.col[t + 1]).
         Every argument is static per (t, flags), so the launch list is recorded once and replayed afterwards."""
-        plan_key = (t, want_logits, greedy, torch.cuda.current_stream().cuda_stream)
+        flags = (want_logits, greedy, torch.cuda.current_stream().cuda_stream)
+        plan_key = (t,) + flags
         plan = st.plans.get(plan_key) if self._plan_cache_enabled else None
         if plan is not None:
             ops.replay(plan)
+            return
+        # Every argument of a decode step is affine in the position t (cache rows, token columns, key count): once three
+        # consecutive recorded steps confirm constant per-argument differences, later positions replay the recorded launch
+        # list with patched arguments instead of re-deriving ~90 launches in Python (the decode loop is launch-bound).
+        aff = st.affine.get(flags) if self._plan_cache_enabled and ops._PROFILE is None else None
+        if aff is not None:
+            if aff[3] is not None:
+                ops.replay_compiled(aff[3], t - aff[0])   # the whole step in one C call
+            else:
+                ops.replay_affine(aff[1], aff[2], t - aff[0])
             return
         if self._plan_cache_enabled:
             ops.begin_record()
@@ -647,7 +659,12 @@ class GPT(nn.Module):
             if greedy:
                 ops.argmax(st.logits, cfg.vocab_size, st.col[t + 1], out_stride=1)
         if self._plan_cache_enabled:
-            st.plans[plan_key] = ops.end_record()
+            plan = st.plans[plan_key] = ops.end_record()
+            p1, p2 = st.plans.get((t - 1,) + flags), st.plans.get((t - 2,) + flags)
+            if p1 is not None and p2 is not None:
+                d1, d2 = ops.plan_deltas(p1, plan), ops.plan_deltas(p2, p1)
+                if d1 is not None and d1 == d2:
+                    st.affine[flags] = (t, plan, d1, ops.compile_affine(plan, d1))
 
     def _sample(self, logits_bf16, out_col, out_stride, temperature, top_k):
         V = self.config.vocab_size

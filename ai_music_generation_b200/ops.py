@@ -63,6 +63,83 @@ def replay(plan):
             _C.check(rc, e[0])
 
 
+def plan_deltas(plan_a, plan_b):
+    """Per-launch argument differences between two recorded plans of the same structure (None if they do not match):
+    [(patch list [(arg index, delta)])].  Decode steps at consecutive positions differ only in arguments that are affine in
+    the position (cache row pointers, token column pointers, the key count), so one recorded step can be replayed at any
+    position by adding k * delta."""
+    if len(plan_a) != len(plan_b):
+        return None
+    out = []
+    for ea, eb in zip(plan_a, plan_b):
+        if ea[0] == "py" or eb[0] == "py" or ea[0] != eb[0] or ea[2] is not eb[2] or len(ea[3]) != len(eb[3]):
+            return None
+        patches = []
+        for i, (x, y) in enumerate(zip(ea[3], eb[3])):
+            if x == y:
+                continue
+            if not (isinstance(x, int) and isinstance(y, int)):
+                return None
+            patches.append((i, y - x))
+        out.append(patches)
+    return out
+
+
+def compile_affine(plan, deltas):
+    """Pack a recorded plan + its per-position argument deltas into the int64 program abcgpt_replay executes in C (one ctypes
+    call per decode step instead of ~90).  Returns (program array, words, launches) or None if a call cannot be encoded."""
+    import ctypes
+    import struct
+    words = []
+    launches = 0
+    for e, patches in zip(plan, deltas):
+        fid = _C.FN_IDS.get(getattr(e[2], "__name__", ""))
+        if fid is None:
+            return None
+        d = dict(patches)
+        words += [fid, len(e[3])]
+        for i, a in enumerate(e[3]):
+            if isinstance(a, float):
+                words += [struct.unpack("<q", struct.pack("<d", a))[0], 0]
+            elif a is None:
+                words += [0, 0]
+            else:
+                v = int(a)
+                if v >= 1 << 63:
+                    v -= 1 << 64
+                words += [v, int(d.get(i, 0))]
+        launches += e[1]
+    arr = (ctypes.c_int64 * len(words))(*words)
+    return arr, len(words), launches
+
+
+def replay_compiled(prog, k):
+    global LAUNCHES
+    arr, n, launches = prog
+    LAUNCHES += launches
+    rc = _C.lib().abcgpt_replay(arr, n, k)
+    if rc != 0:
+        _C.check(rc, "abcgpt_replay")
+
+
+def replay_affine(plan, deltas, k):
+    """Replay `plan` with every patched argument advanced by k * delta (see plan_deltas)."""
+    global LAUNCHES
+    if _PROFILE is not None or _RECORD is not None:
+        raise _C.AbcgptError("replay_affine: not available while profiling / recording")
+    for e, patches in zip(plan, deltas):
+        LAUNCHES += e[1]
+        if patches:
+            args = list(e[3])
+            for i, d in patches:
+                args[i] += k * d
+            rc = e[2](*args)
+        else:
+            rc = e[2](*e[3])
+        if rc != 0:
+            _C.check(rc, e[0])
+
+
 def _call(name, nkernels, meta, fn, *args):
     global LAUNCHES
     LAUNCHES += nkernels

@@ -23,7 +23,7 @@ for alt in (0, 1):
                   f"smem operand bytes {ab}, {ab / cyc:5.1f} B/cyc")
 
 print("CTA pair (cta_group::2), 256 x N x 16, SS K-major")
-for n in (128, 256):
+for n in (64, 128, 256):
     lib.abcgpt_debug_mma_bench(out.data_ptr(), iters, n, -1, 0)
     torch.cuda.synchronize()
     cyc = out.item() / (4 * iters)
