@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.0, help="train with dropout (music configs use 0.2; the headline uses 0 like nanoGPT/bench.py:54)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -189,7 +190,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = wl["cfg"]
+    cfg = dict(wl["cfg"], dropout=args.dropout)
     B = args.batch or wl["batch"]
     T, V = cfg["block_size"], cfg["vocab_size"]
     torch.manual_seed(1337)  # same init on every rank (train.py seeds 1337 + rank, then DDP broadcasts rank 0)
@@ -311,7 +312,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": wl["name"], "global_batch": world * B, "seq_len": T, "parallelism": f"dp{world}",
                    "l2_note": "per-step working set ~11 GB of activations >> 126 MB L2; no explicit flush",
-                   "optimizer": "fused clip_grad_norm_(1.0) + AdamW every step, grad accumulation 1"},
+                   "optimizer": "fused clip_grad_norm_(1.0) + AdamW every step, grad accumulation 1", "dropout": args.dropout},
         "mfu": {"flops_per_token": fpt, "per_gpu_tflops": value / world * fpt / 1e12,
                 "of_nominal_2250": value / world * fpt / 2.25e15,
                 "of_measured_burst": value / world * fpt / (pk["burst"] * 1e12),

@@ -97,3 +97,36 @@ def test_gradsync_two_ranks_gloo():
                          capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("GRADSYNC_OK") == 2
+
+
+def test_affine_plan_deltas_and_program_encoding():
+    """Host logic of the decode replay (ops.plan_deltas / ops.compile_affine): arguments that differ between two recorded steps
+    must be integers with a constant difference; the packed program interleaves (value, delta) per argument."""
+    import struct
+    from ai_music_generation_b200 import _C, ops
+
+    def fake(name):
+        def f(*a):
+            return 0
+        f.__name__ = name
+        return f
+
+    g, ln = fake("abcgpt_gemm_bf16"), fake("abcgpt_layernorm_fwd")
+    plan = lambda t: [("layernorm_fwd", 1, ln, (1000, 2000, 0, 3000, 0, 4000, 5000, 256, 768, 7), (256, 768)),  # noqa: E731
+                      ("gemm", 1, g, (10, 0, 768, 20, 0, 768, 256, 2304, 768, 0, 9000 + 4608 * t, 2304 * 1024, 0, 0, 0, 0, 0, 128, 0,
+                                      0.0, 0, 7), (256, 2304, 768, 0, 0, 0))]
+    d01, d12 = ops.plan_deltas(plan(0), plan(1)), ops.plan_deltas(plan(1), plan(2))
+    assert d01 == d12 == [[], [(10, 4608)]]
+    assert ops.plan_deltas(plan(0), plan(0)[:1]) is None                       # different structure
+    bad = plan(1)
+    bad[1] = bad[1][:3] + (bad[1][3][:19] + (0.5,) + bad[1][3][20:],) + bad[1][4:]
+    assert ops.plan_deltas(plan(0), bad) is None                               # a float argument may not vary
+    arr, n, launches = ops.compile_affine(plan(2), d12)
+    words = list(arr)
+    assert n == len(words) == (2 + 2 * 10) + (2 + 2 * 22) and launches == 2
+    assert words[:2] == [_C.FN_IDS["abcgpt_layernorm_fwd"], 10] and words[2:6] == [1000, 0, 2000, 0]
+    gemm = words[22:]
+    assert gemm[:2] == [_C.FN_IDS["abcgpt_gemm_bf16"], 22]
+    assert gemm[2 + 2 * 10: 4 + 2 * 10] == [9000 + 4608 * 2, 4608]              # the cache row pointer advances per position
+    assert gemm[2 + 2 * 19] == struct.unpack("<q", struct.pack("<d", 0.0))[0]    # floats travel as double bit patterns
+    assert ops.compile_affine([("x", 1, fake("abcgpt_unknown"), (1,), None)], [[]]) is None
