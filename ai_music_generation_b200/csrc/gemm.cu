@@ -25,8 +25,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kNumThreads = 320;  // 1 producer warp + 1 MMA warp + 8 epilogue warps
-constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiWarps = 16;   // four per scheduler: the epilogue arithmetic is dependency-latency bound (ncu: `wait` stalls,
+                                   // IPC 0.15 with two warps per scheduler), so it needs thread-level parallelism, not fewer instructions
+constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;  // 1 producer warp + 1 MMA warp + the epilogue warps
 
 struct GemmParams {
   int M, N, K;
@@ -398,8 +399,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) are visible to this warp
-    const int half = (warp - 2) >> 2;      // which half of the BN columns
-    constexpr int COLS_PER_WARP = BN / 2;
+    const int half = (warp - 2) >> 2;      // which quarter of the BN columns
+    constexpr int COLS_PER_WARP = BN / (kNumEpiWarps / 4);
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int tile = w / p.splits;
@@ -648,8 +649,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int COLS_PER_WARP = BN / 2;
+    const int half = (warp - 2) >> 2;      // which quarter of the BN columns
+    constexpr int COLS_PER_WARP = BN / (kNumEpiWarps / 4);
     int it = 0;
     for (int w = pair_id; w < total_work; w += num_pairs, ++it) {
       const int tile = w / p.splits;
