@@ -1086,11 +1086,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     // latency hides behind a whole step of arithmetic
     const float* stat_src = tid < 64 ? lse : delta;
     const float stat_coef = tid < 64 ? -kLog2e : -kScale;
+    int ls_it = -2, ls_q = 0;            // item decode cached across steps: two integer divisions per item, not per step
+    const float* ls_row = stat_src;
     auto load_stat = [&](int it, int n) {
       float v = 0.f;
       if (it >= 0) {
-        const int qi = ((it / BH) * 2 + n) * 64 + (tid & 63);
-        if (qi < T) v = __ldg(stat_src + static_cast<long long>(it % BH) * T + qi);
+        if (it != ls_it) {
+          ls_it = it;
+          ls_q = (it / BH) * 128 + (tid & 63);
+          ls_row = stat_src + static_cast<long long>(it % BH) * T;
+        }
+        const int qi = ls_q + n * 64;
+        if (qi < T) v = __ldg(ls_row + qi);
       }
       return v;
     };
