@@ -611,18 +611,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
                   int B, int T, int H, int C) {
+  // one warp per token row; a lane reads 16-byte units (8 columns), 8 lanes cover one head (64 columns): 128-bit loads,
+  // three shuffles per head group instead of five per head
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= static_cast<long long>(B) * T) return;
   const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
-  const uint32_t* orow = reinterpret_cast<const uint32_t*>(o + row * C);
-  const uint32_t* drow = reinterpret_cast<const uint32_t*>(dout + row * C);
-  for (int h = 0; h < H; ++h) {
-    const uint32_t a = __ldg(orow + h * 32 + lane), d = __ldg(drow + h * 32 + lane);
-    float s = ptx::bf16lo(a) * ptx::bf16lo(d) + ptx::bf16hi(a) * ptx::bf16hi(d);
+  const uint4* orow = reinterpret_cast<const uint4*>(o + row * C);
+  const uint4* drow = reinterpret_cast<const uint4*>(dout + row * C);
+  const int units = C / 8;  // H * 8
+  for (int u = lane; u < ((units + 31) & ~31); u += 32) {
+    float s = 0.f;
+    if (u < units) {
+      const uint4 a = __ldg(orow + u), d = __ldg(drow + u);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) delta[(static_cast<long long>(b) * H + h) * T + t] = s;
+      for (int e = 0; e < 4; ++e) s += ptx::bf16lo(aw[e]) * ptx::bf16lo(dw[e]) + ptx::bf16hi(aw[e]) * ptx::bf16hi(dw[e]);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if ((lane & 7) == 0 && u < units) delta[(static_cast<long long>(b) * H + (u >> 3)) * T + t] = s;
   }
 }
 
