@@ -141,6 +141,14 @@ __device__ __forceinline__ float fwd_chunk_exp(uint32_t taddr, int lane, float n
   return (acc0.x + acc0.y) + (acc1.x + acc1.y);
 }
 
+// prmt.b32 with a selector whose nibbles have bit 3 set replicates the SIGN of the chosen byte: 0xBB99 turns bits 15 / 31
+// into a bf16x2 AND mask, 0x9999 / 0xBBBB into fp32 masks for the even / odd column of a pair (csrc/dropout.cuh)
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t x, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(sel));
+  return d;
+}
+
 // backward (dQ kernel): dS = P * (dP*scale - delta*scale) for one chunk; row statistics are per thread
 template <int MODE, bool DROP>
 __device__ __forceinline__ void dq_chunk(uint32_t taddr_s, uint32_t taddr_dp, int lane, float neg_lse2, float neg_delta8,
@@ -155,16 +163,19 @@ __device__ __forceinline__ void dq_chunk(uint32_t taddr_s, uint32_t taddr_dp, in
   ptx::tmem_ld32(taddr_dp, dp);
   ptx::tmem_ld_wait();
   const float2 sl = make_float2(kSl2, kSl2), nl = make_float2(neg_lse2, neg_lse2);
-  const float2 sc = make_float2(kScale, kScale), nd = make_float2(neg_delta8, neg_delta8);
+  const float scv = DROP ? kScale * dcfg.inv_keep : kScale;  // dP = (dO V^T) o mask / (1-p): the factor rides on the scale
+  const float2 sc = make_float2(scv, scv), nd = make_float2(neg_delta8, neg_delta8);
+  const uint32_t drop_b = drop_row_key2(drop_rk);
+  const uint32_t drop_s = drop_rk + (static_cast<uint32_t>(kv0) >> 1) * kDropWeyl;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float2 t = __ffma2_rn(f2(s[2 * i], s[2 * i + 1]), sl, nl);
     const float2 p = make_float2(ex2(t.x), ex2(t.y));
     float2 dpe = f2(dp[2 * i], dp[2 * i + 1]);
-    if (DROP) {  // dP = (dO V^T) o mask / (1-p)
-      const uint32_t bits = drop_pair_bits(drop_rk, static_cast<uint32_t>(kv0 + 2 * i) >> 1);
-      dpe.x = drop_keep_lo(bits, dcfg.thr16) ? dpe.x * dcfg.inv_keep : 0.f;
-      dpe.y = drop_keep_hi(bits, dcfg.thr16) ? dpe.y * dcfg.inv_keep : 0.f;
+    if (DROP) {
+      const uint32_t u = attn_drop_signs(attn_drop_fold(drop_s + static_cast<uint32_t>(i) * kDropWeyl, drop_b), dcfg.k15);
+      dpe.x = __uint_as_float(dp[2 * i] & prmt_sign(u, 0x9999u));
+      dpe.y = __uint_as_float(dp[2 * i + 1] & prmt_sign(u, 0xBBBBu));
     }
     const float2 u = __ffma2_rn(dpe, sc, nd);
     float2 d = __fmul2_rn(p, u);
@@ -191,7 +202,11 @@ __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, u
   ptx::tmem_ld32(taddr_s, s);
   ptx::tmem_ld32(taddr_dp, dp);
   ptx::tmem_ld_wait();
-  const float2 sl = make_float2(kSl2, kSl2), sc = make_float2(kScale, kScale);
+  const float scv = DROP ? kScale * dcfg.inv_keep : kScale;  // the 1/(1-p) of dP rides on the scale, that of dV on its epilogue
+  const float2 sl = make_float2(kSl2, kSl2), sc = make_float2(scv, scv);
+  // the mask row is the QUERY (a column here), so every element needs its own hash: lane (kv & 1) of pair kv >> 1
+  const uint32_t drop_off = (static_cast<uint32_t>(kv_t) >> 1) * kDropWeyl;
+  const uint32_t drop_sel = (kv_t & 1) ? 0xBBBBu : 0x9999u;
 #pragma unroll
   for (int i4 = 0; i4 < 8; ++i4) {
     const float4 l4 = lds128(st_lse2 + 16 * i4);     // already negated: -lse*log2e   (ld.shared, broadcast)
@@ -206,16 +221,14 @@ __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, u
       float2 dpe = f2(dp[2 * i], dp[2 * i + 1]);
       float2 pd = p;  // the (dropped) probabilities that multiply dO in dV
       if (DROP) {
-        // the mask row is the QUERY (a column here), so every element needs its own hash: lane (kv & 1) of pair kv >> 1
         uint32_t rk0, rk1;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rk0), "=r"(rk1) : "r"(st_rowkey + 8 * i));
-        const uint32_t sh = (kv_t & 1) * 16, pr = static_cast<uint32_t>(kv_t) >> 1;
-        const bool k0 = ((drop_pair_bits(rk0, pr) >> sh) & 0xFFFFu) >= dcfg.thr16;
-        const bool k1 = ((drop_pair_bits(rk1, pr) >> sh) & 0xFFFFu) >= dcfg.thr16;
-        pd.x = k0 ? p.x * dcfg.inv_keep : 0.f;
-        pd.y = k1 ? p.y * dcfg.inv_keep : 0.f;
-        dpe.x = k0 ? dpe.x * dcfg.inv_keep : 0.f;
-        dpe.y = k1 ? dpe.y * dcfg.inv_keep : 0.f;
+        const uint32_t m0 = prmt_sign(attn_drop_signs(attn_drop_fold(rk0 + drop_off, drop_row_key2(rk0)), dcfg.k15), drop_sel);
+        const uint32_t m1 = prmt_sign(attn_drop_signs(attn_drop_fold(rk1 + drop_off, drop_row_key2(rk1)), dcfg.k15), drop_sel);
+        pd.x = __uint_as_float(__float_as_uint(p.x) & m0);
+        pd.y = __uint_as_float(__float_as_uint(p.y) & m1);
+        dpe.x = __uint_as_float(dp[2 * i] & m0);
+        dpe.y = __uint_as_float(dp[2 * i + 1] & m1);
       }
       const float2 u = __ffma2_rn(dpe, sc, nd);
       float2 d = __fmul2_rn(p, u);
@@ -250,6 +263,8 @@ __device__ __forceinline__ void fwd_chunk(uint32_t taddr, int lane, float neg_m,
   const float2 sl = make_float2(kSl2, kSl2), nm = make_float2(neg_m, neg_m);
   float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
   float m0 = tmax, m1 = -1e30f;
+  const uint32_t drop_b = drop_row_key2(drop_rk);
+  const uint32_t drop_s = drop_rk + (static_cast<uint32_t>(kv0) >> 1) * kDropWeyl;
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
     float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
@@ -268,16 +283,14 @@ __device__ __forceinline__ void fwd_chunk(uint32_t taddr, int lane, float neg_m,
     float2 p1 = make_float2(ex2(t1.x), ex2(t1.y));
     acc0 = __fadd2_rn(acc0, p0);
     acc1 = __fadd2_rn(acc1, p1);
-    if (DROP) {
-      const uint32_t b0 = drop_pair_bits(drop_rk, static_cast<uint32_t>(kv0 + 2 * i) >> 1);
-      const uint32_t b1 = drop_pair_bits(drop_rk, static_cast<uint32_t>(kv0 + 2 * i + 2) >> 1);
-      p0.x = drop_keep_lo(b0, dcfg.thr16) ? p0.x * dcfg.inv_keep : 0.f;
-      p0.y = drop_keep_hi(b0, dcfg.thr16) ? p0.y * dcfg.inv_keep : 0.f;
-      p1.x = drop_keep_lo(b1, dcfg.thr16) ? p1.x * dcfg.inv_keep : 0.f;
-      p1.y = drop_keep_hi(b1, dcfg.thr16) ? p1.y * dcfg.inv_keep : 0.f;
-    }
     pk[i] = ptx::pack_bf16x2(p0.x, p0.y);
     pk[i + 1] = ptx::pack_bf16x2(p1.x, p1.y);
+    if (DROP) {  // AND mask on the packed pair; the 1/(1-p) factor is applied to O in the item epilogue
+      const uint32_t u0 = attn_drop_signs(attn_drop_fold(drop_s + static_cast<uint32_t>(i) * kDropWeyl, drop_b), dcfg.k15);
+      const uint32_t u1 = attn_drop_signs(attn_drop_fold(drop_s + static_cast<uint32_t>(i + 1) * kDropWeyl, drop_b), dcfg.k15);
+      pk[i] &= prmt_sign(u0, 0xBB99u);
+      pk[i + 1] &= prmt_sign(u1, 0xBB99u);
+    }
   }
   tmax = fmaxf(m0, m1);
   rowsum += (acc0.x + acc0.y) + (acc1.x + acc1.y);
@@ -487,7 +500,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::mbar_arrive(&o_free[k & 1]);
       const int t = qt * 128 + r;
       if (t < T) {
-        const float inv = 1.0f / l;
+        const float inv = (DROP ? dcfg.inv_keep : 1.0f) / l;
         __nv_bfloat16* o = out + static_cast<long long>(b * T + t) * C + h * HS;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -1124,6 +1137,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(acc_free);
+      if (DROP && g == 0) {  // dV = (P o mask)^T dO / (1-p)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v0[i] = __float_as_uint(__uint_as_float(v0[i]) * dcfg.inv_keep);
+          v1[i] = __float_as_uint(__uint_as_float(v1[i]) * dcfg.inv_keep);
+        }
+      }
       if (kv_t < T) {
         __nv_bfloat16* o = dqkv + static_cast<long long>(b * T + kv_t) * (3 * C) + (g == 0 ? 2 * C : C) + h * HS;
 #pragma unroll

@@ -42,5 +42,18 @@ def keep_mask(key: int, rows: int, cols: int, p: float, row_offset: int = 0) -> 
 
 
 def attention_keep_mask(key: int, B: int, H: int, T: int, p: float) -> np.ndarray:
-    """bool [B, H, T, T]: row counter (b*H + h)*T + q, column = key position."""
-    return keep_mask(key, B * H * T, T, p).reshape(B, H, T, T)
+    """bool [B, H, T, T]: row counter (b*H + h)*T + q, column = key position.  The attention-probability site uses the
+    cheaper generator of csrc/dropout.cuh (Weyl step + folded 32x32->64 multiply, two 15-bit lanes per word)."""
+    rows = B * H * T
+    thr = np.uint64(0 if p <= 0 else min(32767, int(p * 32768.0 + 0.5)))
+    r = np.arange(rows, dtype=np.uint64) & M32
+    a = _fmix32((np.uint64(key) + r * np.uint64(0x85EBCA77)) & M32)                       # [rows] (= drop_row_key)
+    b = (a * np.uint64(0x9E3779B1) + np.uint64(0x7F4A7C15)) & M32
+    pair = (np.arange((T + 1) // 2, dtype=np.uint64) * np.uint64(0x53C5CA59)) & M32
+    s = (a[:, None] + pair[None, :]) & M32
+    c = (s ^ b[:, None]) * s                                                              # exact: both factors < 2^32
+    h = ((c & M32) ^ (c >> np.uint64(32))) & M32
+    out = np.empty((rows, 2 * pair.shape[0]), dtype=bool)
+    out[:, 0::2] = (h & np.uint64(0x7FFF)) >= thr
+    out[:, 1::2] = ((h >> np.uint64(16)) & np.uint64(0x7FFF)) >= thr
+    return out[:, :T].reshape(B, H, T, T)
