@@ -6,7 +6,7 @@ need a GPU; constructing tensors on / calling the model on anything but a CUDA d
 """
 from .model import GPT, GPTConfig  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
-from .ddp import DDP  # noqa: F401
+from .ddp import DDP, TunesFormerDDP  # noqa: F401
 from .data import DeviceTokenStream  # noqa: F401
 from .tunesformer import TunesFormerShaped  # noqa: F401
 

@@ -14,10 +14,11 @@ import torch
 import torch.distributed as dist
 
 
-def plan_buckets(layer_ranges, head_range, tail_range, bucket_elems):
+def plan_buckets(layer_ranges, head_range, tail_range, bucket_elems, extra_ranges=()):
     """Groups per-layer [lo, hi) element ranges of the flat gradient arena into all-reduce buckets.
 
     layer_ranges[i] is the contiguous range of block i's 2-D gradients; ranges are adjacent and ascending.
+    `extra_ranges`: 2-D tensors registered after the last block (the hierarchical model's patch embedding).
     Returns [(trigger_layer, lo, hi)] in launch order (trigger_layer = the layer whose completion releases the
     bucket; -1 for the final bucket(s) released when the whole backward is done)."""
     buckets = []
@@ -31,19 +32,22 @@ def plan_buckets(layer_ranges, head_range, tail_range, bucket_elems):
         if hi - lo >= bucket_elems or li == 0:
             buckets.append((li, lo, hi))
             hi = None
-    if head_range[1] > head_range[0]:
-        buckets.append((-1, head_range[0], head_range[1]))
-    if tail_range[1] > tail_range[0]:
-        buckets.append((-1, tail_range[0], tail_range[1]))
+    for lo_, hi_ in (head_range, *extra_ranges, tail_range):
+        if hi_ > lo_:
+            buckets.append((-1, lo_, hi_))
     return buckets
 
 
 class GradSync:
-    def __init__(self, grad_flat, layer_ranges, head_range, tail_range, process_group=None, bucket_mb=64.0):
+    def __init__(self, grad_flat, layer_ranges, head_range, tail_range, process_group=None, bucket_mb=64.0,
+                 extra_ranges=(), defer_final=False):
         self.grad = grad_flat
         self.group = process_group
         self.world = dist.get_world_size(process_group)
-        self.buckets = plan_buckets(layer_ranges, head_range, tail_range, int(bucket_mb * 1024 * 1024 / 4))
+        self.buckets = plan_buckets(layer_ranges, head_range, tail_range, int(bucket_mb * 1024 * 1024 / 4), extra_ranges)
+        # defer_final: gradients outside the block stack are still being produced when the stack's backward plan ends
+        # (the patch embedding of the hierarchical model, computed by a later autograd node): the owner calls finalize()
+        self.defer_final = defer_final
         self._by_trigger = {}
         for b in self.buckets:
             self._by_trigger.setdefault(b[0], []).append(b)
@@ -74,6 +78,10 @@ class GradSync:
             self._launch(b)
 
     def backward_done(self):
+        if not self.defer_final:
+            self.finalize()
+
+    def finalize(self):
         for b in self._by_trigger.get(-1, ()):
             self._launch(b)
 
@@ -82,6 +90,25 @@ class GradSync:
             w.wait()  # NCCL: the current stream waits for the collective; the host does not block
         self._pending = []
         self.launched = []
+
+
+def attach_grad_sync(m, process_group=None, bucket_mb=64.0, defer_final=False):
+    """Builds the GradSync of one GPT-shaped module over its flat gradient arena and stores it in m._grad_sync."""
+    m._ensure_device_state()
+    a = m._arena
+    names, offs, params = a["names"], a["offs"], a["params"]
+    end = {n: o + ((p.numel() + 7) // 8) * 8 for n, o, p in zip(names, offs, params)}
+    start = dict(zip(names, offs))
+    layer_ranges = []
+    for i in range(m.config.n_layer):
+        pre = f"transformer.h.{i}."
+        layer_ranges.append((start[pre + "attn.c_attn.weight"], end[pre + "mlp.c_proj.weight"]))
+    head = (0, layer_ranges[0][0]) if layer_ranges else (0, a["n_decay"])
+    extra = [(layer_ranges[-1][1], a["n_decay"])] if layer_ranges else []
+    tail = (a["n_decay"], a["total"])
+    m._grad_sync = GradSync(a["grad"], layer_ranges, head, tail, process_group, bucket_mb, extra_ranges=extra,
+                            defer_final=defer_final)
+    return m._grad_sync
 
 
 class DDP(torch.nn.Module):
@@ -109,20 +136,60 @@ class DDP(torch.nn.Module):
     def _ensure_sync(self):
         m = self.module
         m._ensure_device_state()
-        a = m._arena
-        key = a["grad"].data_ptr()
+        key = m._arena["grad"].data_ptr()
         if self._sync_for == key:
             return
-        names, offs, params = a["names"], a["offs"], a["params"]
-        end = {n: o + ((p.numel() + 7) // 8) * 8 for n, o, p in zip(names, offs, params)}
-        start = dict(zip(names, offs))
-        layer_ranges = []
-        for i in range(m.config.n_layer):
-            pre = f"transformer.h.{i}."
-            layer_ranges.append((start[pre + "attn.c_attn.weight"], end[pre + "mlp.c_proj.weight"]))
-        head = (0, layer_ranges[0][0]) if layer_ranges else (0, a["n_decay"])
-        tail = (a["n_decay"], a["total"])
-        m._grad_sync = GradSync(a["grad"], layer_ranges, head, tail, self._process_group, self._bucket_mb)
+        attach_grad_sync(m, self._process_group, self._bucket_mb)
+        self._sync_for = key
+
+    def forward(self, *args, **kwargs):
+        if dist.is_initialized():
+            self._ensure_sync()
+        return self.module(*args, **kwargs)
+
+    def parameters(self, recurse=True):
+        return self.module.parameters(recurse)
+
+    def clip_grad_norm_(self, max_norm):
+        return self.module.clip_grad_norm_(max_norm)
+
+
+class TunesFormerDDP(torch.nn.Module):
+    """Data parallelism for the hierarchical model (tunesformer.TunesFormerShaped; the reference trains it under
+    torch DataParallel / DDP, tunesformer/train.py): one GradSync per decoder arena.  The character-level decoder's
+    backward runs first and releases its buckets layer by layer, then the patch-level stack's; the patch embedding's
+    gradient is produced by a later autograd node, so that arena's final buckets are released from there
+    (`finalize()`).  clip_grad_norm_ / the optimizer wait on both."""
+
+    def __init__(self, module, process_group=None, bucket_mb=64.0):
+        super().__init__()
+        self.module = module
+        self._process_group = process_group
+        self._bucket_mb = bucket_mb
+        self._sync_for = None
+        if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            for dec in (module.patch_level_decoder, module.char_level_decoder):
+                dist.broadcast(dec._arena["flat"], src=0, group=process_group)
+                dec._shadow_fresh = False
+
+    @property
+    def require_backward_grad_sync(self):
+        return self.module.char_level_decoder.require_backward_grad_sync
+
+    @require_backward_grad_sync.setter
+    def require_backward_grad_sync(self, value):
+        for dec in (self.module.patch_level_decoder, self.module.char_level_decoder):
+            dec.require_backward_grad_sync = bool(value)
+
+    def _ensure_sync(self):
+        p, c = self.module.patch_level_decoder, self.module.char_level_decoder
+        p._ensure_device_state()
+        c._ensure_device_state()
+        key = (p._arena["grad"].data_ptr(), c._arena["grad"].data_ptr())
+        if self._sync_for == key:
+            return
+        attach_grad_sync(c, self._process_group, self._bucket_mb)
+        attach_grad_sync(p, self._process_group, self._bucket_mb, defer_final=True)
         self._sync_for = key
 
     def forward(self, *args, **kwargs):

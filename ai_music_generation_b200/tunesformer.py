@@ -48,6 +48,9 @@ class _PatchEmbed(torch.autograd.Function):
         # runs after the stack's backward plan (autograd order), which has zeroed / attached the gradient arena
         ops.gemm(db16, oh, a_mn=True, b_mn=True, epilogue=ops.EPI_F32_RED, out=dec._view("grad", "patch_embedding.weight"))
         ops.colsum_bf16(db16, dec._view("grad", "patch_embedding.bias"))
+        sync = dec._grad_sync
+        if sync is not None and dec.require_backward_grad_sync:
+            sync.finalize()   # this arena's last gradients: wte/wpe, the patch embedding and the 1-D tail go out now
         return None, None, None
 
 

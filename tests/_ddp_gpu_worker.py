@@ -8,7 +8,60 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ai_music_generation_b200 import DDP, GPT, GPTConfig  # noqa: E402
+from ai_music_generation_b200 import DDP, GPT, GPTConfig, TunesFormerDDP, TunesFormerShaped  # noqa: E402
+
+
+def tunesformer_case(rank, world, dev):
+    """Hierarchical model (BASELINE config 4) under TunesFormerDDP: both arenas' gradients == those of the concatenated
+    batch (every rank's shard has the same pad pattern, so the mean of per-rank mean losses is the global mean), the patch
+    embedding's late gradient is part of the exchange, replicas stay bitwise in sync over optimizer steps."""
+    pc = dict(block_size=16, vocab_size=128, n_layer=2, n_head=2, n_embd=128, dropout=0.0, bias=True, activation="gelu_tanh")
+    cc = dict(block_size=32, vocab_size=128, n_layer=2, n_head=2, n_embd=128, dropout=0.0, bias=True, activation="gelu_tanh")
+    torch.manual_seed(99 + rank)
+    model = TunesFormerShaped(GPTConfig(**pc), GPTConfig(**cc)).to(dev).train()
+    ddp = TunesFormerDDP(model, bucket_mb=0.25)
+    ref = TunesFormerShaped(GPTConfig(**pc), GPTConfig(**cc)).to(dev).train()
+    ref.patch_level_decoder.load_state_dict(model.patch_level_decoder.state_dict())
+    ref.char_level_decoder.load_state_dict(model.char_level_decoder.state_dict())
+    g = torch.Generator().manual_seed(11)
+    Bt = 3
+    lens = torch.randint(6, 33, (Bt, 12), generator=g)
+    shards = []
+    for _ in range(world):
+        pt = torch.randint(3, 128, (Bt, 12, 32), generator=g)
+        pt[torch.arange(32)[None, None, :] >= lens[..., None]] = 0
+        shards.append(pt)
+    full = torch.cat(shards, 0).to(dev)
+    opt = model.configure_optimizers(0.1, 1e-3, (0.9, 0.95))
+    loss = ddp(shards[rank].to(dev))
+    loss.backward()
+    for dec in (model.patch_level_decoder, model.char_level_decoder):
+        dec._grad_sync.wait()
+    torch.cuda.synchronize()
+    ref(full).backward()
+    rels = []
+    for dec, rdec in ((model.patch_level_decoder, ref.patch_level_decoder), (model.char_level_decoder, ref.char_level_decoder)):
+        got, want = dec._arena["grad"], rdec._arena["grad"]
+        rels.append(((got - want).norm() / want.norm()).item())
+        assert rels[-1] < 2e-2, rels
+        pe = [n for n in dec._arena["names"] if n.startswith("patch_embedding")]
+        for n in pe:   # the late gradient took part in the exchange
+            a, b = dec._view("grad", n).float(), rdec._view("grad", n).float()
+            assert ((a - b).norm() / b.norm()).item() < 2e-2, n
+    for _ in range(3):
+        model.clip_grad_norm_(1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        ddp(shards[rank].to(dev)).backward()
+    for dec in (model.patch_level_decoder, model.char_level_decoder):
+        dec._grad_sync.wait()
+        flat = dec._arena["flat"]
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        for other in gathered:
+            assert torch.equal(other, flat), "hierarchical replicas diverged"
+    print(f"DDP_TUNESFORMER_OK rank {rank} rel {rels[0]:.2e} {rels[1]:.2e} buckets "
+          f"{len(model.patch_level_decoder._grad_sync.buckets)}+{len(model.char_level_decoder._grad_sync.buckets)}", flush=True)
 
 
 def main():
@@ -64,6 +117,7 @@ def main():
     for other in gathered:
         assert torch.equal(other, flat), "ranks diverged"
     print(f"DDP_GPU_OK rank {rank} rel {rel:.2e} norm {norm.item():.4f} buckets {len(model._grad_sync.buckets)}", flush=True)
+    tunesformer_case(rank, world, dev)
     dist.destroy_process_group()
 
 

@@ -29,6 +29,23 @@ def main():
     assert sum(hi - lo for lo, hi in order) == total
     assert all(lo >= head for lo, hi in launched_before_tail)
     assert order[0][1] == head + n_layers * per_layer  # the last block is reduced first
+    # deferred final buckets (hierarchical model: the patch embedding's gradient arrives after the stack's backward plan)
+    extra = 64
+    total2 = total + extra
+    grad2 = torch.arange(total2, dtype=torch.float32) * (rank + 1)
+    blocks_end = head + n_layers * per_layer
+    sync2 = GradSync(grad2, layer_ranges, (0, head), (blocks_end + extra, total2), bucket_mb=1024 * 4 / (1024 * 1024),
+                     extra_ranges=[(blocks_end, blocks_end + extra)], defer_final=True)
+    for li in range(n_layers - 1, -1, -1):
+        sync2.layer_done(li)
+    sync2.backward_done()  # must not release the final buckets yet
+    assert all(lo >= head and hi <= blocks_end for lo, hi in sync2.launched)
+    assert torch.equal(grad2[blocks_end:], torch.arange(blocks_end, total2, dtype=torch.float32) * (rank + 1))
+    sync2.finalize()
+    assert sum(hi - lo for lo, hi in sync2.launched) == total2
+    sync2.wait()
+    expect2 = torch.arange(total2, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    assert torch.allclose(grad2, expect2)
     dist.barrier()
     print("GRADSYNC_OK", rank, flush=True)
     dist.destroy_process_group()

@@ -89,6 +89,18 @@ def test_bucket_plan_covers_arena_once():
     assert all(hi - lo >= 2000 for t, lo, hi in buckets[:-3])
 
 
+def test_bucket_plan_extra_range_after_the_last_block():
+    """Hierarchical model: the patch embedding sits between the last block and the 1-D tail of the patch-level arena."""
+    from ai_music_generation_b200.ddp import plan_buckets
+    layer_ranges = [(1000 + 700 * i, 1000 + 700 * (i + 1)) for i in range(3)]
+    buckets = plan_buckets(layer_ranges, (0, 1000), (3600, 3700), bucket_elems=100, extra_ranges=[(3100, 3600)])
+    covered = sorted((lo, hi) for _, lo, hi in buckets)
+    assert covered[0][0] == 0 and covered[-1][1] == 3700
+    for (a, b), (c, d) in zip(covered, covered[1:]):
+        assert b == c
+    assert [(t, lo, hi) for t, lo, hi in buckets if t == -1] == [(-1, 0, 1000), (-1, 3100, 3600), (-1, 3600, 3700)]
+
+
 def test_gradsync_two_ranks_gloo():
     script = os.path.join(ROOT, "tests", "_gloo_gradsync_worker.py")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
