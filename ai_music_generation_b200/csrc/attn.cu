@@ -192,7 +192,7 @@ __device__ __forceinline__ void dq_chunk(uint32_t taddr_s, uint32_t taddr_dp, in
 template <int MODE, bool DROP>
 __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, uint32_t st_lse2, uint32_t st_delta8,
                                           int q_base, int kv_t, int T, uint32_t* pk_p, uint32_t* pk_ds, const DropCfg& dcfg,
-                                          uint32_t st_rowkey) {
+                                          uint32_t st_rowkey, int kv_real) {
   if (MODE == kMasked) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; pk_ds[i] = 0u; }
@@ -205,7 +205,7 @@ __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, u
   const float scv = DROP ? kScale * dcfg.inv_keep : kScale;  // the 1/(1-p) of dP rides on the scale, that of dV on its epilogue
   const float2 sl = make_float2(kSl2, kSl2), sc = make_float2(scv, scv);
   // the mask row is the QUERY (a column here), so every element needs its own hash: lane (kv & 1) of pair kv >> 1
-  const uint32_t drop_off = (static_cast<uint32_t>(kv_t) >> 1) * kDropWeyl;
+  const uint32_t drop_off = (static_cast<uint32_t>(kv_real) >> 1) * kDropWeyl;  // kv_real: key position in its real sequence
   const uint32_t drop_sel = (kv_t & 1) ? 0xBBBBu : 0x9999u;
 #pragma unroll
   for (int i4 = 0; i4 < 8; ++i4) {
@@ -245,6 +245,21 @@ __device__ __forceinline__ void dkv_chunk(uint32_t taddr_s, uint32_t taddr_dp, u
 }
 
 constexpr float kRescaleThreshold = 64.0f;  // log2 units
+
+// Short sequences (T = 32 or 64: the character level of the hierarchical model) are packed 128 / T to a 128-row tile: the
+// kernels see B*T/128 "virtual" sequences of 128 rows and mask block-diagonally (seq_shift = log2 of the real length;
+// kNoPack = not packed).  Row statistics (LSE, delta) and the dropout row counters keep the canonical [B, H, T] indexing of
+// the real sequences, so packing is invisible outside the kernels.
+constexpr int kNoPack = 30;
+__device__ __forceinline__ long long stat_idx(int b, int h, int t, int H, int T, int seq_shift) {
+  if (seq_shift >= kNoPack) return (static_cast<long long>(b) * H + h) * T + t;
+  const int per = T >> seq_shift;
+  return (((static_cast<long long>(b) * per + (t >> seq_shift)) * H + h) << seq_shift) + (t & ((1 << seq_shift) - 1));
+}
+// c0, r0: first column / row of two 32-wide blocks; both lie in the same real sequence?
+__device__ __forceinline__ bool same_seq(int c0, int r0, int seq_shift) { return (c0 >> seq_shift) == (r0 >> seq_shift); }
+// key position inside its real sequence (the dropout mask's column counter)
+__device__ __forceinline__ int real_col(int c, int seq_shift) { return c & ((1 << seq_shift) - 1); }
 
 // p = 2^(s*sl2 - m_ref) for one 32-column chunk, also tracks the raw row max; MODE as for the other chunk helpers
 // DROP: attention dropout (SDPA dropout_p, model.py:64): the row sum uses the undropped probabilities, the P fed to P V is
@@ -298,11 +313,11 @@ __device__ __forceinline__ void fwd_chunk(uint32_t taddr, int lane, float neg_m,
 
 template <bool DROP>
 __device__ __forceinline__ void fwd_tile(uint32_t tm_s, int lane, int cls0, int cls1, float neg_m, float& tmax, float& rowsum,
-                                         uint32_t* pk, const DropCfg& dcfg, uint32_t drop_rk, int kv_tile0) {
+                                         uint32_t* pk, const DropCfg& dcfg, uint32_t drop_rk, int kv_tile0, int seq_shift) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const int cls = c == 0 ? cls0 : cls1;
-    const int kv0 = kv_tile0 + c * 32;
+    const int kv0 = real_col(kv_tile0 + c * 32, seq_shift);
     if (cls == kFull) fwd_chunk<kFull, DROP>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16, dcfg, drop_rk, kv0);
     else if (cls == kDiag) fwd_chunk<kDiag, DROP>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16, dcfg, drop_rk, kv0);
     else fwd_chunk<kMasked, DROP>(tm_s + c * 32, lane, neg_m, tmax, rowsum, pk + c * 16, dcfg, drop_rk, kv0);
@@ -347,7 +362,7 @@ template <bool DROP>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int C, int BH, int nitems,
-                long long* trace, const DropCfg dcfg, long long* cta_trace) {
+                long long* trace, const DropCfg dcfg, long long* cta_trace, int seq_shift) {
   const long long cta_t0 = cta_trace ? globaltimer_ns() : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -520,7 +535,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           w.w = ptx::pack_bf16x2(__uint_as_float(v1[8 * q + 6]) * inv, __uint_as_float(v1[8 * q + 7]) * inv);
           reinterpret_cast<uint4*>(o)[4 + q] = w;
         }
-        lse[(static_cast<long long>(b) * H + h) * T + t] = (m_ref + log2f(l)) * kLn2;
+        lse[stat_idx(b, h, t, H, T, seq_shift)] = (m_ref + log2f(l)) * kLn2;
       }
     };
     bool pend = false;
@@ -536,22 +551,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t tm_O = tmem_base + 128 + (item_k & 1) * 64;
       const int r0 = qt * 128 + quarter * 32;  // first query row of this warp (relative to the sequence)
       float m_ref = 0.f, l = 0.f;
-      const uint32_t drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(bh * T + qt * 128 + r));
+      bool have_ref = false;  // the reference exponent comes from the first tile that has a visible key for this warp
+      const uint32_t drop_rk =
+          DROP ? drop_row_key(dcfg.key, static_cast<uint32_t>(stat_idx(bh / H, bh % H, qt * 128 + r, H, T, seq_shift))) : 0u;
       for (int j = 0; j < num_kv; ++j, ++gt) {
         const int bsel = gt & 1;
         const uint32_t tm_s = tmem_base + lane_off + bsel * 64;
         // chunk classes of this warp for key columns [64j, 64j+32) and [64j+32, 64j+64)
         const int c0 = j * 64, c1 = j * 64 + 32;
-        const int cls0 = (c0 + 31 <= r0) ? kFull : ((c0 > r0 + 31) ? kMasked : kDiag);
-        const int cls1 = (c1 + 31 <= r0) ? kFull : ((c1 > r0 + 31) ? kMasked : kDiag);
+        const int cls0 = !same_seq(c0, r0, seq_shift) ? kMasked : ((c0 + 31 <= r0) ? kFull : ((c0 > r0 + 31) ? kMasked : kDiag));
+        const int cls1 = !same_seq(c1, r0, seq_shift) ? kMasked : ((c1 + 31 <= r0) ? kFull : ((c1 > r0 + 31) ? kMasked : kDiag));
         ATTN_STAMP(0);
         ptx::mbar_wait(&s_full[bsel], (gt >> 1) & 1, 17);
         ptx::tc_fence_after();
         ATTN_STAMP(1);
         uint32_t pk[32];
         float tmax = -1e30f, rowsum = 0.f;
-        if (j == 0) {
-          // first tile: the reference exponent is its true row max (cheap max-only pass, then the exp pass)
+        if (!have_ref && (cls0 != kMasked || cls1 != kMasked)) {
+          have_ref = true;
+          // first tile (with packed short sequences: the first tile of this warp's own sequence): the reference exponent
+          // is its true row max (cheap max-only pass, then the exp pass)
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const int cls = c == 0 ? cls0 : cls1;
@@ -559,9 +578,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             else if (cls == kDiag) tmax = fmaxf(tmax, fwd_chunk_max<kDiag>(tm_s + c * 32, lane));
           }
           m_ref = tmax * kSl2;
-          fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
+          fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64, seq_shift);
         } else {
-          fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
+          fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64, seq_shift);
           const bool need = tmax * kSl2 - m_ref > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
             // rare: raise the reference, rescale the O accumulator in TMEM, recompute this tile's P
@@ -583,7 +602,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             m_ref = m_new;
             tmax = -1e30f;
             rowsum = 0.f;
-            fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64);
+            fwd_tile<DROP>(tm_s, lane, cls0, cls1, -m_ref, tmax, rowsum, pk, dcfg, drop_rk, j * 64, seq_shift);
           }
         }
         l += rowsum;
@@ -623,7 +642,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // ======================================================================================================
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
-                  int B, int T, int H, int C) {
+                  int B, int T, int H, int C, int seq_shift) {
   // one warp per token row; a lane reads 16-byte units (8 columns), 8 lanes cover one head (64 columns): 128-bit loads,
   // three shuffles per head group instead of five per head
   const int lane = threadIdx.x & 31;
@@ -644,7 +663,7 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if ((lane & 7) == 0 && u < units) delta[(static_cast<long long>(b) * H + (u >> 3)) * T + t] = s;
+    if ((lane & 7) == 0 && u < units) delta[stat_idx(b, u >> 3, t, H, T, seq_shift)] = s;
   }
 }
 
@@ -672,7 +691,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                    const __grid_constant__ CUtensorMap tmDO128, const float* __restrict__ lse,
                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, int BH,
-                   int nitems, long long* trace, const DropCfg dcfg, long long* cta_trace) {
+                   int nitems, long long* trace, const DropCfg dcfg, long long* cta_trace, int seq_shift) {
   const long long cta_t0 = cta_trace ? globaltimer_ns() : 0;
   const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
 #define DQ_STAMP(k) do { if (tr && use < 64) trace[use * 8 + (k)] = clock64(); } while (0)
@@ -833,7 +852,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
       if (it < 0) return;
       const int t = (nqt - 1 - it / BH) * 128 + r;
       if (t < T) {
-        const long long idx = static_cast<long long>(it % BH) * T + t;
+        const int bh = it % BH;
+        const long long idx = stat_idx(bh / H, bh % H, t, H, T, seq_shift);
         raw_l = __ldg(lse + idx);
         raw_d = __ldg(delta + idx);
       }
@@ -888,7 +908,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
         neg_d = -nxt_d * kScale;
         const int qt = nqt - 1 - c_it / BH, bh = c_it % BH;
         r0 = qt * 128 + quarter * 32;
-        if (DROP) drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(bh * T + qt * 128 + r));
+        if (DROP) drop_rk = drop_row_key(dcfg.key, static_cast<uint32_t>(stat_idx(bh / H, bh % H, qt * 128 + r, H, T, seq_shift)));
         stat_k = c_k;
         // the next item this group touches is c_k + 1 unless that item has a single step owned by the other group
         int nk = c_k + 1;
@@ -910,9 +930,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
         const int c0 = c_n * 64 + c * 32;
         const uint32_t ta_s = tbuf + c * 32, ta_dp = ta_s + 64;
         uint32_t pk[16];
-        if (c0 + 31 <= r0) dq_chunk<kFull, DROP>(ta_s, ta_dp, lane, neg_l, neg_d, pk, dcfg, drop_rk, c0);
-        else if (c0 > r0 + 31) dq_chunk<kMasked, DROP>(ta_s, ta_dp, lane, neg_l, neg_d, pk, dcfg, drop_rk, c0);
-        else dq_chunk<kDiag, DROP>(ta_s, ta_dp, lane, neg_l, neg_d, pk, dcfg, drop_rk, c0);
+        const int cr = real_col(c0, seq_shift);
+        if (c0 > r0 + 31 || !same_seq(c0, r0, seq_shift)) dq_chunk<kMasked, DROP>(ta_s, ta_dp, lane, neg_l, neg_d, pk, dcfg, drop_rk, cr);
+        else if (c0 + 31 <= r0) dq_chunk<kFull, DROP>(ta_s, ta_dp, lane, neg_l, neg_d, pk, dcfg, drop_rk, cr);
+        else dq_chunk<kDiag, DROP>(ta_s, ta_dp, lane, neg_l, neg_d, pk, dcfg, drop_rk, cr);
         // dS chunk c (32 key columns = 16 packed words) overwrites score columns that this thread has already consumed
         ptx::tmem_st16(tbuf + c * 16, pk);
       }
@@ -954,7 +975,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                     const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
                     const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int C, int BH,
-                    int nitems, long long* trace, const DropCfg dcfg, long long* cta_trace) {
+                    int nitems, long long* trace, const DropCfg dcfg, long long* cta_trace, int seq_shift) {
   const long long cta_t0 = cta_trace ? globaltimer_ns() : 0;
   const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
 #define DKV_STAMP(k) do { if (tr && use < 64) trace[512 + use * 8 + (k)] = clock64(); } while (0)
@@ -1108,7 +1129,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     // latency hides behind a whole step of arithmetic
     const float* stat_src = tid < 64 ? lse : delta;
     const float stat_coef = tid < 64 ? -kLog2e : -kScale;
-    int ls_it = -2, ls_q = 0;            // item decode cached across steps: two integer divisions per item, not per step
+    int ls_it = -2, ls_q = 0, ls_bh = 0;  // item decode cached across steps: two integer divisions per item, not per step
     const float* ls_row = stat_src;
     auto load_stat = [&](int it, int n) {
       float v = 0.f;
@@ -1116,10 +1137,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         if (it != ls_it) {
           ls_it = it;
           ls_q = (it / BH) * 128 + (tid & 63);
-          ls_row = stat_src + static_cast<long long>(it % BH) * T;
+          ls_bh = it % BH;
+          ls_row = stat_src + static_cast<long long>(ls_bh) * T;
         }
         const int qi = ls_q + n * 64;
-        if (qi < T) v = __ldg(ls_row + qi);
+        if (qi < T) v = __ldg(seq_shift >= kNoPack ? ls_row + qi : stat_src + stat_idx(ls_bh / H, ls_bh % H, qi, H, T, seq_shift));
       }
       return v;
     };
@@ -1197,7 +1219,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       float* st_lse = stat + (g * 2 + (use & 1)) * 192;
       st_lse[tid] = raw_cur * stat_coef;
       if (DROP && tid < 64)
-        st_lse[128 + tid] = __uint_as_float(drop_row_key(dcfg.key, static_cast<uint32_t>(bh * T + q0 + tid)));
+        st_lse[128 + tid] = __uint_as_float(
+            drop_row_key(dcfg.key, static_cast<uint32_t>(stat_idx(bh / H, bh % H, q0 + tid, H, T, seq_shift))));
       raw_cur = load_stat(a_it, a_n);  // next own step: consumed at the top of the next iteration
       DKV_STAMP(1);
       ptx::bar_sync(1 + g, 128);
@@ -1211,9 +1234,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         const uint32_t ta_s = tbuf + c * 32, ta_dp = ta_s + 64;
         const uint32_t l2 = ptx::smem_u32(st_lse) + c * 128, d8 = l2 + 256, rkeys = l2 + 512;
         uint32_t pk_p[16], pk_ds[16];
-        if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p, pk_ds, dcfg, rkeys);
-        else if (c0 + 31 < r0 || c0 >= T) dkv_chunk<kMasked, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p, pk_ds, dcfg, rkeys);
-        else dkv_chunk<kDiag, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p, pk_ds, dcfg, rkeys);
+        const int kvr = real_col(kv_t, seq_shift);
+        if (c0 + 31 < r0 || c0 >= T || !same_seq(c0, r0, seq_shift)) dkv_chunk<kMasked, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p, pk_ds, dcfg, rkeys, kvr);
+        else if (c0 > r0 && c0 + 31 < T) dkv_chunk<kFull, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p, pk_ds, dcfg, rkeys, kvr);
+        else dkv_chunk<kDiag, DROP>(ta_s, ta_dp, l2, d8, c0, kv_t, T, pk_p, pk_ds, dcfg, rkeys, kvr);
         // P^T / dS^T chunk c (32 query columns = 16 packed words each) overwrite score columns already consumed
         ptx::tmem_st16(tbuf + c * 16, pk_p);
         ptx::tmem_st16(tbuf + 64 + c * 16, pk_ds);
@@ -1250,6 +1274,17 @@ int set_smem(K kern, int bytes) {
   return 0;
 }
 
+// sequences of 32 or 64 positions are packed to 128-row virtual sequences when the batch fills whole tiles (see kNoPack)
+int pack_short(int& B, int& T) {
+  if ((T == 32 || T == 64) && (static_cast<long long>(B) * T) % 128 == 0) {
+    const int shift = T == 32 ? 5 : 6;
+    B = static_cast<int>(static_cast<long long>(B) * T / 128);
+    T = 128;
+    return shift;
+  }
+  return kNoPack;
+}
+
 int check_shape(const char* who, int B, int T, int H) {
   ABCGPT_CHECK_ARG(B > 0 && T > 0 && H > 0, "%s: bad shape B=%d T=%d H=%d", who, B, T, H);
   ABCGPT_CHECK_ARG(static_cast<long long>(B) * H * ((T + 127) / 128) < (1ll << 30), "%s: too many (tile, batch*head) items", who);
@@ -1266,6 +1301,7 @@ int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float 
   ABCGPT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "attn_fwd: dropout p must be in [0, 1)");
   const int C = H * HS;
   const DropCfg dcfg = make_drop(drop_p, drop_key);
+  const int seq_shift = pack_short(B, T);
   CUtensorMap tmQ, tmKV;
   if ((rc = encode_tmap_2d(&tmQ, qkv, 2, 3ull * C, static_cast<uint64_t>(B) * T, 3ull * C * 2, 64, 128, true))) return rc;
   if ((rc = encode_tmap_2d(&tmKV, qkv, 2, 3ull * C, static_cast<uint64_t>(B) * T, 3ull * C * 2, 64, 64, true))) return rc;
@@ -1280,10 +1316,10 @@ int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float 
   long long* CT = g_attn_cta_trace;
   if (dcfg.thr16 == 0)
     attn_fwd_kernel<false><<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
-                                                                       T, H, C, BH, nitems, g_attn_trace, dcfg, CT);
+                                                                       T, H, C, BH, nitems, g_attn_trace, dcfg, CT, seq_shift);
   else
     attn_fwd_kernel<true><<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
-                                                                      T, H, C, BH, nitems, g_attn_trace, dcfg, CT);
+                                                                      T, H, C, BH, nitems, g_attn_trace, dcfg, CT, seq_shift);
   return launch_status("attn_fwd_kernel");
 }
 
@@ -1295,6 +1331,7 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
   ABCGPT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "attn_bwd: dropout p must be in [0, 1)");
   const int C = H * HS;
   const DropCfg dcfg = make_drop(drop_p, drop_key);
+  const int seq_shift = pack_short(B, T);
   const uint64_t rows = static_cast<uint64_t>(B) * T;
   CUtensorMap tmQKV128, tmQKV64, tmDO128, tmDO64;
   if ((rc = encode_tmap_2d(&tmQKV128, qkv, 2, 3ull * C, rows, 3ull * C * 2, 64, 128, true))) return rc;
@@ -1312,7 +1349,7 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
   {
     const long long nrows = static_cast<long long>(B) * T;
     attn_delta_kernel<<<static_cast<int>((nrows + 7) / 8), 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T, H, C);
+        reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T, H, C, seq_shift);
     if ((rc = launch_status("attn_delta_kernel"))) return rc;
   }
   const int BH = B * H, nitems = ((T + 127) / 128) * BH;
@@ -1322,16 +1359,16 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
   long long* CT2 = g_attn_cta_trace ? g_attn_cta_trace + 8 * 1024 : nullptr;
   if (dcfg.thr16 == 0) {
     attn_bwd_dkv_kernel<false><<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
-                                                                              BH, nitems, g_attn_trace, dcfg, CT1);
+                                                                              BH, nitems, g_attn_trace, dcfg, CT1, seq_shift);
     if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
     attn_bwd_dq_kernel<false><<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
-                                                                            BH, nitems, g_attn_trace, dcfg, CT2);
+                                                                            BH, nitems, g_attn_trace, dcfg, CT2, seq_shift);
   } else {
     attn_bwd_dkv_kernel<true><<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
-                                                                             BH, nitems, g_attn_trace, dcfg, CT1);
+                                                                             BH, nitems, g_attn_trace, dcfg, CT1, seq_shift);
     if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
     attn_bwd_dq_kernel<true><<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
-                                                                           BH, nitems, g_attn_trace, dcfg, CT2);
+                                                                           BH, nitems, g_attn_trace, dcfg, CT2, seq_shift);
   }
   return launch_status("attn_bwd_dq_kernel");
 }

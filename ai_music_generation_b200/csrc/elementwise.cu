@@ -50,21 +50,49 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float4* 
   }
 }
 
-// dwpe[t,:] += sum_b dx[b,t,:]  (deterministic: one thread per (t, 4 columns), loops over the batch)
+// dwpe[t,:] += sum_b dx[b,t,:]: one thread per (t, 4 columns) loops over a slice of the batch.  With long sequences one
+// slice covers the whole batch (deterministic read-modify-write); short sequences with huge batches (the character level
+// of the hierarchical model: T = 32, B ~ 8000) have too few (t, column) pairs to fill the GPU, so the batch is cut into
+// gridDim.y slices that add their partial sums with vector reductions.
 __global__ void embed_bwd_wpe_kernel(const float4* __restrict__ dx, float4* __restrict__ dwpe, int B, int T, int C4,
-                                     DropCfg drop) {
+                                     int per_slice, DropCfg drop) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(T) * C4) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long stride = static_cast<long long>(T) * C4;
-  for (int b = 0; b < B; ++b) {
+  const int b0 = blockIdx.y * per_slice, b1 = min(B, b0 + per_slice);
+  const uint32_t trow = static_cast<uint32_t>(i / C4);
+  const int c = static_cast<int>(i % C4);
+  int b = b0;
+  for (; b + 1 < b1; b += 2) {  // two independent chains
+    float4 v = __ldg(dx + b * stride + i), w = __ldg(dx + (b + 1) * stride + i);
+    drop4(v, drop, static_cast<uint32_t>(b * T) + trow, c);
+    drop4(w, drop, static_cast<uint32_t>((b + 1) * T) + trow, c);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    acc2.x += w.x; acc2.y += w.y; acc2.z += w.z; acc2.w += w.w;
+  }
+  if (b < b1) {
     float4 v = __ldg(dx + b * stride + i);
-    drop4(v, drop, static_cast<uint32_t>(b * T + i / C4), static_cast<int>(i % C4));
+    drop4(v, drop, static_cast<uint32_t>(b * T) + trow, c);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  float4 o = dwpe[i];
-  o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
-  dwpe[i] = o;
+  acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
+  if (gridDim.y == 1) {
+    float4 o = dwpe[i];
+    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+    dwpe[i] = o;
+  } else {
+    ptx::red_add_v4(reinterpret_cast<float*>(dwpe + i), acc.x, acc.y, acc.z, acc.w);
+  }
+}
+// batch slices for the kernel above: enough blocks for ~8 per SM, at least 16 sequences per slice
+static void wpe_slices(int B, long long n, int* slices, int* per_slice) {
+  const long long blocks_x = (n + 127) / 128;
+  long long want = (8ll * sm_count() + blocks_x - 1) / blocks_x;
+  if (want > B / 16) want = B / 16;
+  if (want < 1) want = 1;
+  *per_slice = static_cast<int>((B + want - 1) / want);
+  *slices = (B + *per_slice - 1) / *per_slice;
 }
 
 // dwte[idx[m],:] += dx[m,:].  The ABC vocabulary has ~95 rows, so thousands of tokens collide on each row:
@@ -517,8 +545,10 @@ int embed_bwd(const int64_t* idx, const float* dx, float* dwte, float* dwpe, int
   const int C4 = C / 4;
   {
     const long long n = static_cast<long long>(T) * C4;
-    embed_bwd_wpe_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, stream>>>(
-        reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dwpe), M / T, T, C4, drop);
+    int slices, per_slice;
+    wpe_slices(M / T, n, &slices, &per_slice);
+    embed_bwd_wpe_kernel<<<dim3(static_cast<unsigned>((n + 127) / 128), slices), 128, 0, stream>>>(
+        reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dwpe), M / T, T, C4, per_slice, drop);
     int rc = launch_status("embed_bwd_wpe_kernel");
     if (rc) return rc;
   }
@@ -557,8 +587,10 @@ int set_first_pos(const float* first, const float* wpe, float* x, int B, int T, 
 int pos_bwd(const float* dx, float* dwpe, int M, int T, int C, cudaStream_t stream) {
   ABCGPT_CHECK_ARG(dx && dwpe && M > 0 && T > 0 && M % T == 0 && C % 4 == 0, "pos_bwd: bad arguments");
   const long long n = static_cast<long long>(T) * (C / 4);
-  embed_bwd_wpe_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, stream>>>(
-      reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dwpe), M / T, T, C / 4, make_drop(0.f, 0));
+  int slices, per_slice;
+  wpe_slices(M / T, n, &slices, &per_slice);
+  embed_bwd_wpe_kernel<<<dim3(static_cast<unsigned>((n + 127) / 128), slices), 128, 0, stream>>>(
+      reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dwpe), M / T, T, C / 4, per_slice, make_drop(0.f, 0));
   return launch_status("embed_bwd_wpe_kernel");
 }
 int onehot_bf16(const int64_t* tok, void* out, int M, int S, int V, cudaStream_t stream) {

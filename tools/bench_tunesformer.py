@@ -20,6 +20,7 @@ ap.add_argument("--tunes", type=int, default=64)
 ap.add_argument("--patches", type=int, default=128)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--breakdown", action="store_true", help="extra instrumented pass: per-kernel-family milliseconds per step")
 args = ap.parse_args()
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(local)
@@ -67,11 +68,25 @@ if world > 1:
     t = torch.tensor([ms], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
+fam = None
+if args.breakdown:
+    prof = []
+    ops.set_profile(prof)
+    step()
+    torch.cuda.synchronize()
+    ops.set_profile(None)
+    fam = {}
+    for name, meta, a0, a1 in prof:
+        key = name
+        if name == "gemm":
+            key = {(0, 0): "gemm_fwd", (0, 1): "gemm_dgrad", (1, 1): "gemm_wgrad"}.get((meta[3], meta[4]), "gemm")
+        fam[key] = round(fam.get(key, 0.0) + a0.elapsed_time(a1), 3)
 chars = world * B * (P - 1) * 32
 n_params = sum(p.numel() for p in model.parameters())
 if rank == 0:
     print(json.dumps({"n_gpus": world, "workload": f"TunesFormer-shaped 9L(T=128 patches)+3L(T=32 chars) 768d, {B} tunes x {P} patches x 32 chars",
                       "ms_per_step": ms, "chars_per_s": chars / ms * 1e3, "patches_per_s": world * B * P / ms * 1e3,
-                      "params": n_params, "gpu_launches_per_step": (ops.LAUNCHES - l0) // args.steps, "loss": loss.item()}))
+                      "params": n_params, "gpu_launches_per_step": (ops.LAUNCHES - l0) // args.steps, "loss": loss.item(),
+                      **({"kernel_breakdown_ms": fam} if fam else {})}))
 if world > 1:
     dist.destroy_process_group()

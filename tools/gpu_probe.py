@@ -372,6 +372,11 @@ def build_cases():
     cases["attn_t256"] = lambda: case_attn("attn_t256", 2, 256, 3, True, timing=False)
     cases["attn_t1024"] = lambda: case_attn("attn_t1024", 2, 1024, 2, True, timing=False)
     cases["attn_t32"] = lambda: case_attn("attn_t32", 3, 32, 2, True, timing=False)
+    # short sequences packed 4 / 2 to a 128-row tile (batch fills whole tiles), and a ragged batch that does not pack
+    cases["attn_t32_packed"] = lambda: case_attn("attn_t32_packed", 12, 32, 2, True, timing=False)
+    cases["attn_t64_packed"] = lambda: case_attn("attn_t64_packed", 6, 64, 3, True, timing=False)
+    cases["attn_t64"] = lambda: case_attn("attn_t64", 3, 64, 2, True, timing=False)
+    cases["attn_perf_cfg4_char"] = lambda: case_attn("attn_perf_cfg4_char", 8192, 32, 12, True)
     cases["attn_t200"] = lambda: case_attn("attn_t200", 2, 200, 2, True, timing=False)
     cases["attn_spike"] = lambda: case_attn("attn_spike", 2, 320, 2, True, timing=False, spike=True)
     cases["attn_perf_cfg2"] = lambda: case_attn("attn_perf_cfg2", 64, 256, 6, True)
