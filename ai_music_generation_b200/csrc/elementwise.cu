@@ -379,18 +379,38 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
   if (tid < 64) q[tid] = __bfloat162float(base[static_cast<long long>(n_keys - 1) * 3 * C + h * 64 + tid]) * 0.125f;
   __syncthreads();
   float mx = -INFINITY;
-  for (int k = tid; k < n_keys; k += 128) {
-    const uint4* kr = reinterpret_cast<const uint4*>(base + static_cast<long long>(k) * 3 * C + C + h * 64);
-    float s = 0.f;
+  {
+    // scores: eight lanes share a key (16 bytes = 8 head dimensions each), so one warp instruction reads four whole 128-byte
+    // K rows; 16 keys in flight per warp.  (One thread per key read 16 bytes from 32 different lines per instruction: the
+    // L1 tag stage, one line per clock, capped that at ~4.5 TB/s chip-wide.)
+    const int sub = lane & 7, grp = lane >> 3;
+    float qr[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint4 v = __ldg(kr + j);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int e = 0; e < 8; ++e) qr[e] = q[sub * 8 + e];
+    const __nv_bfloat16* kbase = base + C + h * 64 + sub * 8;
+    for (int k0 = warp * 16; k0 < n_keys; k0 += 64) {
+      uint4 v[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) s += q[8 * j + 2 * e] * ptx::bf16lo(w[e]) + q[8 * j + 2 * e + 1] * ptx::bf16hi(w[e]);
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * 4 + grp;
+        v[u] = k < n_keys ? __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<long long>(k) * 3 * C)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float sc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sc += qr[2 * e] * ptx::bf16lo(w[e]) + qr[2 * e + 1] * ptx::bf16hi(w[e]);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+        const int k = k0 + u * 4 + grp;
+        if (k < n_keys) {
+          if (sub == 0) prob[k] = sc;
+          mx = fmaxf(mx, sc);
+        }
+      }
     }
-    prob[k] = s;
-    mx = fmaxf(mx, s);
   }
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
@@ -411,25 +431,38 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
   // every fourth key, a lane two adjacent columns (one 128 B row segment per warp instruction), four keys in flight per warp.
   const uint32_t* vbase = reinterpret_cast<const uint32_t*>(base + 2 * C + h * 64) + lane;
   const long long vstride = 3ll * C / 2;  // row stride in 32-bit words
-  float a0 = 0.f, a1 = 0.f;
+  float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
   int k = warp;
+  // eight keys in flight per warp: with four (24 KB per SM at 12 resident blocks) this phase was latency-bound, below the
+  // ~35 KB per SM that HBM latency x bandwidth asks for
+  for (; k + 28 < n_keys; k += 32) {
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(vbase + (k + 4 * u) * vstride);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) {
+      const float p0 = ptx::bf16_round(prob[k + 4 * u] * inv), p1 = ptx::bf16_round(prob[k + 4 * u + 4] * inv);
+      a0 += p0 * ptx::bf16lo(v[u]); a1 += p0 * ptx::bf16hi(v[u]);
+      c0 += p1 * ptx::bf16lo(v[u + 1]); c1 += p1 * ptx::bf16hi(v[u + 1]);
+    }
+  }
   for (; k + 12 < n_keys; k += 16) {
     const uint32_t v0 = __ldg(vbase + k * vstride), v1 = __ldg(vbase + (k + 4) * vstride);
     const uint32_t v2 = __ldg(vbase + (k + 8) * vstride), v3 = __ldg(vbase + (k + 12) * vstride);
     const float p0 = ptx::bf16_round(prob[k] * inv), p1 = ptx::bf16_round(prob[k + 4] * inv);
     const float p2 = ptx::bf16_round(prob[k + 8] * inv), p3 = ptx::bf16_round(prob[k + 12] * inv);
     a0 += p0 * ptx::bf16lo(v0); a1 += p0 * ptx::bf16hi(v0);
-    a0 += p1 * ptx::bf16lo(v1); a1 += p1 * ptx::bf16hi(v1);
+    c0 += p1 * ptx::bf16lo(v1); c1 += p1 * ptx::bf16hi(v1);
     a0 += p2 * ptx::bf16lo(v2); a1 += p2 * ptx::bf16hi(v2);
-    a0 += p3 * ptx::bf16lo(v3); a1 += p3 * ptx::bf16hi(v3);
+    c0 += p3 * ptx::bf16lo(v3); c1 += p3 * ptx::bf16hi(v3);
   }
   for (; k < n_keys; k += 4) {
     const uint32_t v0 = __ldg(vbase + k * vstride);
     const float p0 = ptx::bf16_round(prob[k] * inv);
     a0 += p0 * ptx::bf16lo(v0); a1 += p0 * ptx::bf16hi(v0);
   }
-  part[warp][2 * lane] = a0;
-  part[warp][2 * lane + 1] = a1;
+  part[warp][2 * lane] = a0 + c0;
+  part[warp][2 * lane + 1] = a1 + c1;
   __syncthreads();
   if (tid < 64)
     out[static_cast<long long>(b) * C + h * 64 + tid] =
