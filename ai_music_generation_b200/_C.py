@@ -46,6 +46,7 @@ _SIGNATURES = {
     "abcgpt_sample_batch": (c_int, [_P, c_int, c_int64, _P, _P, _P, c_int, c_int, _P]),
     "abcgpt_colsum_bf16": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "abcgpt_replay": (c_int, [_P, c_int64, c_int64]),
+    "abcgpt_set_pdl": (c_int, [c_int]),
     "abcgpt_debug_gemm_stats": (c_int, [_P]),
     "abcgpt_debug_attn_trace": (c_int, [_P]),
     "abcgpt_debug_attn_cta_trace": (c_int, [_P]),

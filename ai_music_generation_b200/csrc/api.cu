@@ -162,6 +162,14 @@ int abcgpt_replay(const int64_t* prog, int64_t n_words, int64_t k) {
 #undef MP_
 #undef I_
 
+/* Programmatic dependent launch for subsequent launches of this process (GEMM, attention, LayerNorm, decode attention):
+ * the next kernel's CTAs become resident and run their prologue while the previous kernel drains.  Pays on chains of small
+ * kernels (a decoded token); default off. */
+int abcgpt_set_pdl(int on) {
+  abcgpt::set_pdl(on != 0);
+  return 0;
+}
+
 /* debug: device pointer to 8 uint64 cycle counters filled by subsequent GEMM launches (NULL disables) */
 int abcgpt_debug_gemm_stats(void* device_counters) {
   abcgpt::g_gemm_stats = reinterpret_cast<unsigned long long*>(device_counters);

@@ -410,6 +410,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::uniform(*tmem_slot);  // S buffers at columns [0,64) and [64,128); O buffers at [128,192) and [192,256)
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
+  ptx::pdl_wait();               // everything above touched only this CTA's shared memory / TMEM
 
   // number of 64-row K/V tiles of an item
   auto tiles_of = [&](int it) {
@@ -643,6 +645,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
                   int B, int T, int H, int C, int seq_shift) {
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
+  ptx::pdl_wait();
   // one warp per token row; a lane reads 16-byte units (8 columns), 8 lanes cover one head (64 columns): 128-bit loads,
   // three shuffles per head group instead of five per head
   const int lane = threadIdx.x & 31;
@@ -743,6 +747,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::uniform(*tmem_slot);
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
+  ptx::pdl_wait();               // everything above touched only this CTA's shared memory / TMEM
   const uint32_t tm_dQ = tmem_base + 128 * kSBuf;  // score buffer b: S at 128 b, dP at 128 b + 64; dQ buffers at 384, 448
 
   // number of 64-row K/V tiles of an item (item -> query tile nqt-1-rank: heaviest first)
@@ -1027,6 +1033,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::uniform(*tmem_slot);
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
+  ptx::pdl_wait();               // everything above touched only this CTA's shared memory / TMEM
   const uint32_t tm_dV = tmem_base + 128 * kSBuf, tm_dK = tm_dV + 64;  // score buffer b: S^T at 128 b, dP^T at 128 b + 64
 
   // item -> key tile kt = rank (tile 0 sees every query tile: heaviest first); steps = 64-row query tiles from 2 kt on
@@ -1315,10 +1323,10 @@ int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float 
   const int grid = nitems < 2 * sm_count() ? nitems : 2 * sm_count();  // persistent: two CTAs per SM
   long long* CT = g_attn_cta_trace;
   if (dcfg.thr16 == 0)
-    attn_fwd_kernel<false><<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
+    launch_k(attn_fwd_kernel<false>, dim3(grid), dim3(kThreads), FwdSmem::TOTAL, stream, tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
                                                                        T, H, C, BH, nitems, g_attn_trace, dcfg, CT, seq_shift);
   else
-    attn_fwd_kernel<true><<<grid, kThreads, FwdSmem::TOTAL, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
+    launch_k(attn_fwd_kernel<true>, dim3(grid), dim3(kThreads), FwdSmem::TOTAL, stream, tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), lse,
                                                                       T, H, C, BH, nitems, g_attn_trace, dcfg, CT, seq_shift);
   return launch_status("attn_fwd_kernel");
 }
@@ -1358,16 +1366,16 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
   long long* CT1 = g_attn_cta_trace ? g_attn_cta_trace + 4 * 1024 : nullptr;
   long long* CT2 = g_attn_cta_trace ? g_attn_cta_trace + 8 * 1024 : nullptr;
   if (dcfg.thr16 == 0) {
-    attn_bwd_dkv_kernel<false><<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
+    launch_k(attn_bwd_dkv_kernel<false>, dim3(grid), dim3(kBwdThreads), DkvSmem::TOTAL, stream, tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
                                                                               BH, nitems, g_attn_trace, dcfg, CT1, seq_shift);
     if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
-    attn_bwd_dq_kernel<false><<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
+    launch_k(attn_bwd_dq_kernel<false>, dim3(grid), dim3(kBwdThreads), DqSmem::TOTAL, stream, tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
                                                                             BH, nitems, g_attn_trace, dcfg, CT2, seq_shift);
   } else {
-    attn_bwd_dkv_kernel<true><<<grid, kBwdThreads, DkvSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
+    launch_k(attn_bwd_dkv_kernel<true>, dim3(grid), dim3(kBwdThreads), DkvSmem::TOTAL, stream, tmQKV128, tmQKV64, tmDO64, lse, delta, dq, T, H, C,
                                                                              BH, nitems, g_attn_trace, dcfg, CT1, seq_shift);
     if ((rc = launch_status("attn_bwd_dkv_kernel"))) return rc;
-    attn_bwd_dq_kernel<true><<<grid, kBwdThreads, DqSmem::TOTAL, stream>>>(tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
+    launch_k(attn_bwd_dq_kernel<true>, dim3(grid), dim3(kBwdThreads), DqSmem::TOTAL, stream, tmQKV128, tmQKV64, tmDO128, lse, delta, dq, T, H, C,
                                                                            BH, nitems, g_attn_trace, dcfg, CT2, seq_shift);
   }
   return launch_status("attn_bwd_dq_kernel");

@@ -39,6 +39,30 @@ inline int launch_status(const char* what) {
 // ---- device info ---------------------------------------------------------------------------------
 int sm_count();  // SM count of the current device (cached per device)
 
+// ---- programmatic dependent launch -----------------------------------------------------------------
+// The step is a chain of ~250 (training) / ~90 (one decoded token) dependent kernels on one stream.  Kernels launched
+// through launch_k carry the programmatic-stream-serialization attribute: their CTAs may become resident as soon as every
+// CTA of the previous kernel has executed griddepcontrol.launch_dependents (first instruction of our kernels) or exited,
+// run their prologue (barrier init, TMEM allocation, descriptor prefetch) and then block in griddepcontrol.wait until the
+// previous grid has completed and its memory is visible.  Launch latency and prologues leave the critical path; ordering
+// of every global access is unchanged (all of them sit behind the wait).  Off unless requested (set_pdl, see common.cu).
+bool pdl_enabled();
+void set_pdl(bool on);
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
 // ---- TMA descriptors -----------------------------------------------------------------------------
 // 2D bf16/fp32 row-major matrix [outer, inner] with row pitch `row_bytes`; box = [box_outer, box_inner];
 // 128-byte swizzle (box_inner * elem_bytes must be 128) or none.

@@ -369,6 +369,8 @@ colsum_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, int M, int N, 
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __restrict__ out, int Tmax, int n_keys, int H,
                    int C) {
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
+  ptx::pdl_wait();
   extern __shared__ float prob[];  // [n_keys]
   __shared__ float q[64];
   __shared__ float red[4];
@@ -704,7 +706,7 @@ int attn_decode(const void* cache, void* out, int B, int Tmax, int n_keys, int H
       done = true;
     }
   }
-  attn_decode_kernel<<<B * H, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(cache),
+  launch_k(attn_decode_kernel, dim3(B * H), dim3(128), smem, stream, reinterpret_cast<const __nv_bfloat16*>(cache),
                                                    reinterpret_cast<__nv_bfloat16*>(out), Tmax, n_keys, H, H * 64);
   return launch_status("attn_decode_kernel");
 }

@@ -303,6 +303,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::uniform(*tmem_slot);
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
+  ptx::pdl_wait();               // everything above touched only this CTA's shared memory / TMEM
 
   const int total_work = p.num_m_blk * p.num_n_blk * p.splits;
   const long long t_start = p.stats ? clock64() : 0;
@@ -448,7 +450,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
     ABCGPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, kNumThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  launch_k(kern, dim3(grid), dim3(kNumThreads), C::SMEM_BYTES, stream, tmA, tmB, p);
   return launch_status("gemm_kernel");
 }
 
@@ -543,6 +545,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   ptx::cluster_sync_all();  // barrier inits + TMEM allocations of BOTH CTAs are visible before anything is signalled
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::uniform(*tmem_slot);
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
+  ptx::pdl_wait();               // everything above touched only this CTA's shared memory / TMEM
 
   const int num_m_pair = (p.num_m_blk + 1) / 2;
   const int m_units = QUAD ? num_m_pair / 2 : num_m_pair;  // QUAD: the host guarantees an even number of 256-row tiles
@@ -698,11 +702,13 @@ int launch2q(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p
   constexpr int CL = QUAD ? 4 : 2;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see launch_k (common.h)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = Cfg2::SMEM_BYTES;
   cfg.stream = stream;
@@ -717,6 +723,7 @@ int launch2q(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p
   }
   const long long clusters = units < max_clusters ? units : max_clusters;
   cfg.gridDim = dim3(static_cast<unsigned>(CL * clusters));
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   ABCGPT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   return launch_status("gemm2_kernel");
 }

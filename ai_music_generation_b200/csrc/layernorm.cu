@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
               __nv_bfloat16* __restrict__ y, float* __restrict__ yf, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int M, int C) {
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
+  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -82,6 +84,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
               float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ dw, float* __restrict__ db,
               int M, int C, DropCfg drop) {
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
+  ptx::pdl_wait();
   extern __shared__ float red[];  // [kWarpsPerBlock][C] dweight partials (+ [kWarpsPerBlock][C] dbias partials)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -214,7 +218,7 @@ int layernorm_fwd(const float* x, const float* weight, const float* bias, void* 
   ABCGPT_CHECK_ARG(x && weight && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
   const int nv = (C + 127) / 128;
   const int grid = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  LN_DISPATCH(nv, (ln_fwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+  LN_DISPATCH(nv, (launch_k(ln_fwd_kernel<NV>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream, 
                       x, weight, bias, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, C)));
   return launch_status("ln_fwd_kernel");
 }
@@ -234,9 +238,8 @@ int layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, cons
   LN_DISPATCH(nv, {
     auto launch = [&](auto kern) -> int {
       if (smem > 48 * 1024) ABCGPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-      kern<<<grid, kWarpsPerBlock * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, weight, mean,
-                                                        rstd, dresid_in, dx_out,
-                                                        reinterpret_cast<__nv_bfloat16*>(dx_bf16), dweight, dbias, M, C, drop);
+      launch_k(kern, dim3(grid), dim3(kWarpsPerBlock * 32), smem, stream, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x,
+               weight, mean, rstd, dresid_in, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dweight, dbias, M, C, drop);
       return 0;
     };
     int rc = has_bias ? launch(ln_bwd_kernel<NV, true>) : launch(ln_bwd_kernel<NV, false>);

@@ -348,4 +348,13 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// programmatic dependent launch (see launch_k in common.h)
+#ifndef ABCGPT_NO_PDL
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else  // A/B builds only: kernels without the two instructions must never be launched with the attribute
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_wait() {}
+#endif
+
 }  // namespace ptx

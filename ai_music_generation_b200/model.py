@@ -716,6 +716,7 @@ class GPT(nn.Module):
                 st.col[:T0].copy_(idx.t())
                 greedy = top_k is not None and min(top_k, self.config.vocab_size) == 1
                 stopped = False
+                ops.set_pdl(True)   # ~90 small dependent launches per token: overlap each launch / prologue with its predecessor
                 for t in range(last):
                     want = t >= T0 - 1
                     self._decode_step(st, t, want, greedy and want)
@@ -726,6 +727,7 @@ class GPT(nn.Module):
                             st.col[t + 2:last + 1].fill_(stop_token)
                             stopped = True
                             break
+                ops.set_pdl(False)
                 out[:, :last + 1].copy_(st.col[:last + 1].t())
                 if stopped:
                     out[:, last + 1:].fill_(stop_token)
@@ -737,5 +739,6 @@ class GPT(nn.Module):
                 bufs = self._forward_plan(cond, None, keep_activations=False)
                 self._sample(bufs.last_logits, out[:, pos + 1:], out.stride(0), temperature, top_k)
         finally:
+            ops.set_pdl(False)
             self.train(was_training)
         return out

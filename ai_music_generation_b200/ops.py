@@ -37,6 +37,11 @@ def end_record():
     return plan
 
 
+def set_pdl(on):
+    """Programmatic dependent launch for the launches that follow (include/abcgpt.h: abcgpt_set_pdl)."""
+    _C.lib().abcgpt_set_pdl(1 if on else 0)
+
+
 def record_callback(fn):
     """Interleave a Python callback (e.g. DDP bucket launch) with the recorded launches; runs now and on every replay."""
     if _RECORD is not None:
