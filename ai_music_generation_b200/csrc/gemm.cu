@@ -13,6 +13,9 @@
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 #include "common.h"
+#include <stdlib.h>
+#include <mutex>
+#include <vector>
 #include "dropout.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -43,6 +46,7 @@ struct GemmParams {
   int act_tanh;  // GELU / DGELU epilogues: 0 = exact erf (nn.GELU()), 1 = tanh form (HF "gelu_new", TunesFormer's GPT-2 blocks)
   int wide;  // 1: every epilogue pointer / leading dimension is 32-byte aligned -> 256-bit global accesses
   DropCfg drop;  // RESID epilogue only: dropout on the Linear output before the residual add (model.py:75-76,91)
+  int* sched;  // pair kernel: global ticket counter of the dynamic tile scheduler (nullptr = static round-robin)
   unsigned long long* stats;  // optional debug counters (cycles): [0] producer empty-wait, [1] mma full-wait,
                               // [2] mma tmem-empty wait, [3] epilogue tmem-full wait, [4] epilogue busy, [5] cta total
 };
@@ -495,9 +499,23 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = 6;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int SCHED_SLOTS = 16;               // ring of published work ids (dynamic tile scheduler)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 + 1024;
 };
 
+// Dynamic tile scheduler (non-QUAD, opt-in: ABCGPT_DYNAMIC_TILES=1).  The static round-robin `w = pair, pair + num_pairs, ...`
+// assumes every CTA pair is resident from the start; a pair that starts late (its SMs held by another stream's kernel, e.g.
+// an NCCL all-reduce) delays the whole GEMM.  Here the first tile of a pair stays static (no atomic round trip on a launch's
+// critical path: with it the 147 GEMM launches of a step lost 0.4 ms), from the second on the leader's producer warp draws
+// tickets from a global counter while it issues the previous tile's loads and publishes them to both CTAs through a 16-slot
+// shared-memory ring with one mbarrier per slot (plain store + arrive locally; st.async + complete_tx to the peer, so every
+// waiter uses an ordinary CTA-scope wait — a cluster-scope acquire wait costs a CCTL.IVALL per waiter); the value is
+// broadcast with __shfl_sync so the issue loops stay on the uniform datapath.  Producer, MMA and epilogue warps read the
+// ring at their own pace (never more than ~9 tiles apart: operand ring + two accumulators + the prefetched ticket).
+// Resident pairs absorb the tiles of late ones; every pair draws exactly one end ticket, so the pair holding the last one
+// resets the counter for the next launch.  MEASURED: parity-green, but no gain — 4-GPU DDP step 26.0 ms with either
+// schedule (the all-reduce cost that overlap fails to hide, ~0.9 of 1.1 ms, is therefore NOT late GEMM pairs), one GPU
+// 25.65 vs 25.48 ms.  Kept for experiments with other co-running kernels.
 // QUAD: clusters of FOUR CTAs = two CTA pairs working on vertically adjacent 256-row tiles of the same 256 output columns.
 // Both pairs need the same B (weight) k-blocks, so each CTA fetches only HALF of its 128 B rows and multicasts them to the
 // CTA with the same role in the other pair: the L2 -> SM operand traffic per FLOP drops by a quarter.  That traffic is what
@@ -516,6 +534,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* sched_id = reinterpret_cast<uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 192);     // [SCHED_SLOTS]
+  uint64_t* sched_full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + 256);  // [SCHED_SLOTS]
 
   const int warp = ptx::uniform(threadIdx.x >> 5);  // provably warp-uniform: the issuer loops below stay on the uniform datapath
   const int lane = threadIdx.x & 31;
@@ -535,6 +555,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::mbar_init(&tfull[s], 1);
       ptx::mbar_init(&tempty[s], 2 * kNumEpiWarps);
     }
+    for (int s = 0; s < C::SCHED_SLOTS; ++s) ptx::mbar_init(&sched_full[s], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -555,6 +576,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const long long t_start = p.stats ? clock64() : 0;
   long long w0 = 0, w1 = 0;
   const int num_pairs = gridDim.x / CL;
+  // dynamic scheduling from the SECOND tile of a pair on: the first one is static (w = pair index), so a launch does not
+  // start with an atomic round trip plus a message to the peer CTA on its critical path (147 GEMM launches per step)
+  const bool dyn = !QUAD && p.sched != nullptr && total_work > num_pairs;
+  const int dyn_work = total_work - num_pairs;  // tickets [0, dyn_work) map to work items num_pairs + ticket
+  // work item of iteration `it` of this pair (-1: none left)
+  auto next_work = [&](int it) -> int {
+    if (!dyn) {
+      const int w = pair_id + it * num_pairs;
+      return w < total_work ? w : -1;
+    }
+    if (it == 0) return pair_id;
+    const int slot = it & (C::SCHED_SLOTS - 1);
+    ptx::mbar_wait(&sched_full[slot], (it / C::SCHED_SLOTS) & 1, 45);
+    // a value loaded from shared memory is not provably warp-uniform: without the broadcast the TMA / MMA issue loops that
+    // derive coordinates and trip counts from it fall off the uniform datapath (ptx.cuh, "Warp-uniform issue")
+    return static_cast<int>(ptx::uniform(ptx::ld_shared_u32_volatile(&sched_id[slot])));
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -562,7 +600,41 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool issue = ptx::elect_one();  // whole warp runs the loop, one elected lane issues (uniform operands)
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = pair_id; w < total_work; w += num_pairs) {
+      // leader: a ticket is drawn while the previous tile's loads are being issued and published (to both CTAs) once they
+      // are: the atomic's round trip is never waited for (its result is first touched a whole tile after it was issued)
+      bool drew_end = false;
+      int pending = -1;
+      auto draw = [&]() -> int {
+        if (drew_end) return -1;
+        return atomicAdd(p.sched, 1);
+      };
+      auto post = [&](int i, int w) {  // work id of iteration i -> both CTAs' rings
+        const int slot = i & (C::SCHED_SLOTS - 1);
+        ptx::st_shared_u32_volatile(&sched_id[slot], static_cast<uint32_t>(w));
+        ptx::mbar_arrive(&sched_full[slot]);  // own CTA: plain store + release arrive
+        const uint32_t peer_bar = ptx::mapa(ptx::smem_u32(&sched_full[slot]), crank ^ 1u);
+        ptx::mbar_arrive_expect_tx_cluster(peer_bar, 4);  // peer CTA: the word travels with its own completion
+        ptx::st_async_u32(ptx::mapa(ptx::smem_u32(&sched_id[slot]), crank ^ 1u), static_cast<uint32_t>(w), peer_bar);
+      };
+      auto publish = [&](int i, int w) {
+        if (w >= 0) {
+          if (w == dyn_work + num_pairs - 1) atomicExch(p.sched, 0);  // the last ticket of this launch
+          if (w >= dyn_work) {
+            w = -1;
+            drew_end = true;
+          } else {
+            w += num_pairs;
+          }
+        }
+        post(i, w);
+      };
+      if (dyn && leader && issue) {
+        pending = draw();    // ticket of iteration 1
+        post(0, pair_id);    // nobody waits for slot 0 now (iteration 0 is static), but its phase must advance for iteration 16
+      }
+      for (int it = 0;; ++it) {
+        const int w = next_work(it);
+        if (w < 0) break;
         const int split = w % p.splits;
         const int tile = w / p.splits;
         const int m_unit = tile / p.num_n_blk;
@@ -601,6 +673,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             phase ^= 1;
           }
         }
+        if (dyn && leader && issue) {  // this tile's loads are out: hand the next work item to both CTAs, draw one more
+          publish(it + 1, pending);
+          pending = draw();
+        }
       }
       if (issue && p.stats) atomicAdd(&p.stats[0], static_cast<unsigned long long>(w0));
     }
@@ -613,8 +689,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int w = pair_id; w < total_work; w += num_pairs, ++it) {
+      for (int it = 0;; ++it) {
+        const int w = next_work(it);
+        if (w < 0) break;
         const int split = w % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
@@ -655,8 +732,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;      // which quarter of the BN columns
     constexpr int COLS_PER_WARP = BN / (kNumEpiWarps / 4);
-    int it = 0;
-    for (int w = pair_id; w < total_work; w += num_pairs, ++it) {
+    for (int it = 0;; ++it) {
+      const int w = next_work(it);
+      if (w < 0) break;
       const int tile = w / p.splits;
       const int m_unit = tile / p.num_n_blk;
       const int m0 = (QUAD ? 2 * m_unit + static_cast<int>(pr) : m_unit) * 256 + static_cast<int>(rank) * 128;
@@ -745,6 +823,34 @@ int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const
     case ABCGPT_EPI_F32: return launch2<A_MN, B_MN, ABCGPT_EPI_F32>(tmA, tmB, p, grid, quad, stream);
   }
   return fail(-1, "unknown GEMM epilogue %d", epi);
+}
+
+// one ticket counter per (device, stream) that has launched a pair GEMM (kernels on one stream run one after another; two
+// streams must not share a counter).  Opt-in (ABCGPT_DYNAMIC_TILES=1): measured neutral under 4-GPU data parallelism
+// (26.0 ms either way) and -0.7 % on one GPU, see the comment above gemm2_kernel.
+int* sched_counter(cudaStream_t stream) {
+  struct Entry { int dev; cudaStream_t st; int* ptr; };
+  static std::mutex mu;
+  static std::vector<Entry> pool;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("ABCGPT_DYNAMIC_TILES");
+    enabled = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Entry& e : pool)
+    if (e.dev == dev && e.st == stream) return e.ptr;
+  if (pool.size() >= 256) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
+  int* ptr = nullptr;
+  if (cudaMalloc(&ptr, 128) != cudaSuccess) return nullptr;
+  if (cudaMemset(ptr, 0, 128) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+  pool.push_back({dev, stream, ptr});
+  return ptr;
 }
 
 int dispatch_major2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
@@ -840,7 +946,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   p.M = M; p.N = N; p.K = K;
   p.num_m_blk = num_m_blk; p.num_n_blk = num_n_blk; p.num_k_blk = num_k_blk;
   p.splits = splits; p.kb_per_split = kb_per_split;
-  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.act_tanh = act_tanh; p.stats = g_gemm_stats; p.drop = make_drop(drop_p, drop_key);
+  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.act_tanh = act_tanh; p.sched = (pair && !quad) ? sched_counter(stream) : nullptr; p.stats = g_gemm_stats; p.drop = make_drop(drop_p, drop_key);
   {
     const bool f32_out = (epi == ABCGPT_EPI_RESID || epi == ABCGPT_EPI_F32 || epi == ABCGPT_EPI_F32_RED);
     const long long cb = f32_out ? 4 : 2, ab = (epi == ABCGPT_EPI_RESID) ? 4 : 2;

@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.0, help="train with dropout (music configs use 0.2; the headline uses 0 like nanoGPT/bench.py:54)")
+    ap.add_argument("--bucket-mb", type=float, default=64.0,
+                    help="gradient all-reduce bucket size (N > 1); a huge value = one exposed all-reduce after the backward")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -200,7 +202,7 @@ def main():
         model = GPT(GPTConfig(**cfg)).to(dev)
         opt = model.configure_optimizers(0.1, wl["lr"], wl["betas"], "cuda")
     model.train()
-    net = DDP(model) if world > 1 else model
+    net = DDP(model, bucket_mb=args.bucket_mb) if world > 1 else model
 
     g = torch.Generator().manual_seed(1234 + rank)
     n_host = 4
