@@ -610,6 +610,58 @@ class GPT(nn.Module):
         flops_per_iter = flops_per_token * T * fwdbwd_per_iter
         return flops_per_iter * (1.0 / dt) / flops_promised
 
+    def _generate_ragged(self, idx, prompt_lens, max_new_tokens, temperature, top_k, stop_token, stop_check_every):
+        if not idx.is_cuda:
+            raise _C.AbcgptError("GPT.generate: idx must be a CUDA tensor (there is no CPU path)")
+        B, Tmax = idx.shape
+        lens = torch.as_tensor(prompt_lens, device=idx.device, dtype=torch.int64).view(B)
+        lmin, lmax = int(lens.min()), int(lens.max())
+        bs = self.config.block_size
+        total = lmax + max_new_tokens
+        if lmin < 1 or lmax > Tmax:
+            raise ValueError(f"prompt_lens must lie in [1, {Tmax}]")
+        if total - 1 > bs:
+            raise ValueError(f"ragged generation needs max(prompt_lens) + max_new_tokens <= block_size + 1 (got {total} > {bs + 1}); "
+                             "group the prompts by length instead")
+        fill = 0 if stop_token is None else int(stop_token)
+        out = torch.full((B, total), fill, device=idx.device, dtype=torch.int64)
+        was_training = self.training
+        self.eval()
+        try:
+            self._ensure_device_state()
+            key = ("decode", B, bs)
+            if key not in self._bufs:
+                self._bufs[key] = _DecodeState(self.config, B, bs, idx.device)
+            st = self._bufs[key]
+            pos = torch.arange(total, device=idx.device).view(-1, 1)            # [total, 1]
+            is_prompt = pos < lens.view(1, -1)                                    # [total, B]
+            forced = torch.zeros(total, B, device=idx.device, dtype=torch.int64)
+            forced[:lmax] = idx[:, :lmax].t()
+            st.col[:lmin].copy_(forced[:lmin])
+            greedy = top_k is not None and min(top_k, self.config.vocab_size) == 1
+            last = total - 1
+            ops.set_pdl(True)
+            for t in range(last):
+                want = t >= lmin - 1
+                self._decode_step(st, t, want, greedy and want)
+                if want and not greedy:
+                    self._sample(st.logits, st.col[t + 1], 1, temperature, top_k)
+                if want and t + 1 < lmax:   # rows still inside their prompt take the prompt token, the others keep the sampled one
+                    st.col[t + 1].copy_(torch.where(is_prompt[t + 1], forced[t + 1], st.col[t + 1]))
+                if stop_token is not None and t >= lmin and (t - lmin) % stop_check_every == stop_check_every - 1:
+                    seen = ((st.col[:t + 2] == stop_token) & ~is_prompt[:t + 2]).any(dim=0)
+                    if bool(seen.all()):
+                        last = t + 1
+                        break
+            ops.set_pdl(False)
+            out[:, :last + 1] = st.col[:last + 1].t()
+            beyond = pos.view(1, -1) >= (lens + max_new_tokens).view(-1, 1)      # [B, total]
+            out.masked_fill_(beyond, fill)
+        finally:
+            ops.set_pdl(False)
+            self.train(was_training)
+        return out
+
     def _decode_step(self, st, t, want_logits, greedy):
         """Position t of every sequence (tokens st.col[t]).  Appends this position's q|k|v to the cache and, if
         want_logits, leaves the next-token logits in st.logits (greedy: also writes the argmax into st.col[t + 1]).
@@ -683,7 +735,8 @@ class GPT(nn.Module):
             out_col[:, 0].copy_(nxt)
 
     @torch.no_grad()
-    def generate(self, idx, max_new_tokens, temperature=1.0, top_k=None, use_cache=True, stop_token=None, stop_check_every=64):
+    def generate(self, idx, max_new_tokens, temperature=1.0, top_k=None, use_cache=True, stop_token=None, stop_check_every=64,
+                 prompt_lens=None):
         """Reference semantics (model.py:305-330): feed the sequence back max_new_tokens times, last-position logits,
         temperature, optional top-k, sample, append; the context is cropped to block_size.
 
@@ -694,7 +747,17 @@ class GPT(nn.Module):
 
         stop_token (extension, default off): sample.py cuts every generated tune at the first end-of-tune symbol
         (sample.py:163-165), so once EVERY sequence of the batch has produced it the remaining steps cannot change the
-        written files; checked every `stop_check_every` tokens (one host sync each), the tail is filled with stop_token."""
+        written files; checked every `stop_check_every` tokens (one host sync each), the tail is filled with stop_token.
+
+        prompt_lens (extension, default off; SURVEY.md 8f N3 "variable-length prompt batching"): idx is right-padded
+        [B, max prompt length] and row i holds prompt_lens[i] real tokens.  Positions are absolute, so all rows advance
+        through the same position t together; a row whose prompt is longer than t + 1 takes its next token from the
+        prompt instead of the sampler (its prefix is fed through the same single-position steps an equal-length batch
+        uses, so each row's tokens are those of generating it alone).  Row i of the result holds its prompt followed by
+        max_new_tokens generated tokens; anything after that is filled with stop_token (0 if None).  Needs
+        max(prompt_lens) + max_new_tokens <= block_size + 1 (the window may not slide)."""
+        if prompt_lens is not None:
+            return self._generate_ragged(idx, prompt_lens, max_new_tokens, temperature, top_k, stop_token, stop_check_every)
         if not idx.is_cuda:
             raise _C.AbcgptError("GPT.generate: idx must be a CUDA tensor (there is no CPU path)")
         B, T0 = idx.shape

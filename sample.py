@@ -4,8 +4,9 @@
 
 Same settings (reference sample.py:17-42), same checkpoint / meta.pkl contracts (sample.py:55-100), same prompt
 construction from a validation set (first `n_conditional_measures` bars; sample.py:108-142), same output normalisation
-(cut at '$', trim to the last bar line; sample.py:158-169).  Difference: prompts of equal length are decoded as one batch
-through GPT.generate (the reference decodes them one at a time through the same batch-generic API, model.py:305-330).
+(cut at '$', trim to the last bar line; sample.py:158-169).  Difference: prompts are decoded in batches through GPT.generate,
+also when their lengths differ (prompt_lens; the reference decodes them one at a time through the same batch-generic API,
+model.py:305-330).
 """
 from __future__ import annotations
 
@@ -97,22 +98,42 @@ def main():
     out_dir = os.path.join(s["out_dir"], "samples")
     os.makedirs(out_dir, exist_ok=True)
     todo = [(key, text, encode(text)) for key, text in prompts_from(s)]
-    by_len = {}
-    for item in todo:
-        by_len.setdefault(len(item[2]), []).append(item)
     top_k = s["top_k"] if s["top_k"] > 0 else None
+    block = model.config.block_size
+    # prompts sorted by length and cut into batches; a batch of different lengths is decoded together (prompt_lens: rows
+    # still inside their prompt are fed its tokens) as long as the longest prompt + max_new_tokens fits the context window,
+    # otherwise it falls back to equal-length groups (the window slides: reference-style recompute per group)
+    todo.sort(key=lambda item: len(item[2]))
+    chunks = []
+    for i in range(0, len(todo), s["batch"]):
+        chunk = todo[i:i + s["batch"]]
+        lens = [len(ids) for _, _, ids in chunk]
+        if len(set(lens)) == 1 or max(lens) + s["max_new_tokens"] <= block + 1:
+            chunks.append(chunk)
+        else:
+            by_len = {}
+            for item in chunk:
+                by_len.setdefault(len(item[2]), []).append(item)
+            chunks.extend(group for _, group in sorted(by_len.items()))
     with torch.no_grad():
-        for _, group in sorted(by_len.items()):
-            for i in range(0, len(group), s["batch"]):
-                chunk = group[i:i + s["batch"]]
+        for chunk in chunks:
+            lens = [len(ids) for _, _, ids in chunk]
+            if len(set(lens)) == 1:
                 x = torch.tensor([ids for _, _, ids in chunk], dtype=torch.long, device=s["device"])
                 y = model.generate(x, s["max_new_tokens"], temperature=s["temperature"], top_k=top_k, stop_token=stop).tolist()
-                for (key, text, _), ids in zip(chunk, y):
-                    res = decode(ids)
-                    print(f"\nPrefix: {text}\nGeneration: {res}\n" + "-" * 50)
-                    name = f"sample_{key}.abc" if abc else f"sample_{key}.txt"
-                    with open(os.path.join(out_dir, name), "w") as f:
-                        f.write(normalise(res, key, abc))
+            else:
+                x = torch.zeros(len(chunk), max(lens), dtype=torch.long)
+                for r, (_, _, ids) in enumerate(chunk):
+                    x[r, :len(ids)] = torch.tensor(ids, dtype=torch.long)
+                y = model.generate(x.to(s["device"]), s["max_new_tokens"], temperature=s["temperature"], top_k=top_k,
+                                   stop_token=stop, prompt_lens=lens).tolist()
+                y = [row[:n + s["max_new_tokens"]] for row, n in zip(y, lens)]
+            for (key, text, _), ids in zip(chunk, y):
+                res = decode(ids)
+                print(f"\nPrefix: {text}\nGeneration: {res}\n" + "-" * 50)
+                name = f"sample_{key}.abc" if abc else f"sample_{key}.txt"
+                with open(os.path.join(out_dir, name), "w") as f:
+                    f.write(normalise(res, key, abc))
 
 
 if __name__ == "__main__":

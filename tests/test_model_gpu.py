@@ -312,6 +312,42 @@ def test_generate_early_stop_is_output_equivalent(cuda_device):
     assert bool((early[:, -1] == s).all())   # the batch stopped early and the tail was filled
 
 
+def test_generate_ragged_prompts_equal_one_at_a_time(cuda_device):
+    """generate(prompt_lens=...) (variable-length prompt batching): a right-padded batch of prompts of
+    different lengths is decoded together; every row must carry exactly the tokens of generating that prompt alone (greedy:
+    identical token ids — the per-row arithmetic of the decode kernels does not depend on the batch), followed by the fill."""
+    g = load("tiny")
+    cfg = O.OracleConfig(**g["spec"]["cfg"])          # block_size 64
+    sd = O.synthetic_state(cfg, seed=1)
+    model = make_model(g["spec"]["cfg"], sd, cuda_device).eval()
+    torch.manual_seed(3)
+    lens = [3, 9, 9, 1, 14, 6]
+    n_new = 40
+    padded = torch.zeros(len(lens), max(lens), dtype=torch.long)
+    prompts = []
+    for r, n in enumerate(lens):
+        prompts.append(torch.randint(1, cfg.vocab_size, (1, n)))
+        padded[r, :n] = prompts[-1][0]
+    out = model.generate(padded.to(cuda_device), n_new, top_k=1, prompt_lens=lens).cpu()
+    assert out.shape == (len(lens), max(lens) + n_new)
+    for r, n in enumerate(lens):
+        alone = model.generate(prompts[r].to(cuda_device), n_new, top_k=1).cpu()[0]
+        assert torch.equal(out[r, :n + n_new], alone), (r, n)
+        assert bool((out[r, n + n_new:] == 0).all())
+    # per-row stop: the batch ends once every row has produced the stop token AFTER its own prompt
+    gen = [out[r, n:n + n_new] for r, n in enumerate(lens)]
+    common = [t for t in range(cfg.vocab_size) if all(bool((x[:24] == t).any()) for x in gen)]
+    if common:
+        s_tok = common[0]
+        early = model.generate(padded.to(cuda_device), n_new, top_k=1, prompt_lens=lens, stop_token=s_tok, stop_check_every=8).cpu()
+        for r, n in enumerate(lens):
+            first = n + int((gen[r] == s_tok).nonzero()[0])
+            assert torch.equal(early[r, : first + 1], out[r, : first + 1])
+        assert bool((early[:, -1] == s_tok).all())
+    with pytest.raises(ValueError):
+        model.generate(padded.to(cuda_device), 60, top_k=1, prompt_lens=lens)   # 14 + 60 > block_size + 1
+
+
 def test_tunesformer_shaped_hierarchical_model_matches_bf16_oracle(cuda_device):
     """BASELINE config 4 end to end: patch-level decoder (one-hot patch embedding GEMM, inputs_embeds stack,
     hidden states out) feeding the first input embedding of the char-level decoder, HF-shifted loss that ignores pad
