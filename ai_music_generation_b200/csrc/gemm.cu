@@ -182,9 +182,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
   if (p.bias != nullptr) {
+    if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0) {
+      // every thread of the warp reads the same 32 columns: eight broadcast 128-bit loads instead of 32 scalar ones
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+    }
   }
   const int ncols = min(32, p.N - col0);  // multiple of 8 (host-checked)
 
