@@ -377,8 +377,11 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
   __shared__ float part[4][64];
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const __nv_bfloat16* base = cache + static_cast<long long>(b) * Tmax * 3 * C;
-  if (tid < 64) q[tid] = __bfloat162float(base[static_cast<long long>(n_keys - 1) * 3 * C + h * 64 + tid]) * 0.125f;
+  // head-major cache [B, 3H, Tmax, 64] (q heads | k heads | v heads): the K and V rows of one (b, h) are contiguous, so both
+  // phases stream whole DRAM pages instead of 128-byte pieces 4.6 KB apart
+  const long long head = static_cast<long long>(Tmax) * 64;
+  const __nv_bfloat16* base = cache + static_cast<long long>(b) * 3 * H * head;
+  if (tid < 64) q[tid] = __bfloat162float(base[h * head + static_cast<long long>(n_keys - 1) * 64 + tid]) * 0.125f;
   __syncthreads();
   float mx = -INFINITY;
   {
@@ -389,13 +392,13 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
     float qr[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) qr[e] = q[sub * 8 + e];
-    const __nv_bfloat16* kbase = base + C + h * 64 + sub * 8;
+    const __nv_bfloat16* kbase = base + (H + h) * head + sub * 8;
     for (int k0 = warp * 16; k0 < n_keys; k0 += 64) {
       uint4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int k = k0 + u * 4 + grp;
-        v[u] = k < n_keys ? __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<long long>(k) * 3 * C)) : make_uint4(0u, 0u, 0u, 0u);
+        v[u] = k < n_keys ? __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<long long>(k) * 64)) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -431,8 +434,8 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
   const float inv = 1.0f / ((red[0] + red[1]) + (red[2] + red[3]));
   // out[d] = sum_k p_k V[k][d]: the flash kernels round P to bf16 before the second matmul; mirror that.  Each warp takes
   // every fourth key, a lane two adjacent columns (one 128 B row segment per warp instruction), four keys in flight per warp.
-  const uint32_t* vbase = reinterpret_cast<const uint32_t*>(base + 2 * C + h * 64) + lane;
-  const long long vstride = 3ll * C / 2;  // row stride in 32-bit words
+  const uint32_t* vbase = reinterpret_cast<const uint32_t*>(base + (2 * H + h) * head) + lane;
+  const long long vstride = 32;  // row stride in 32-bit words
   float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
   int k = warp;
   // eight keys in flight per warp: with four (24 KB per SM at 12 resident blocks) this phase was latency-bound, below the

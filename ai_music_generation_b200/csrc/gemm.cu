@@ -46,6 +46,7 @@ struct GemmParams {
   int act_tanh;  // GELU / DGELU epilogues: 0 = exact erf (nn.GELU()), 1 = tanh form (HF "gelu_new", TunesFormer's GPT-2 blocks)
   int wide;  // 1: every epilogue pointer / leading dimension is 32-byte aligned -> 256-bit global accesses
   DropCfg drop;  // RESID epilogue only: dropout on the Linear output before the residual add (model.py:75-76,91)
+  long long head_stride;  // BF16 epilogue: != 0 -> column c of a row goes to (c / 64) * head_stride + c % 64 (head-major KV cache)
   int* sched;  // pair kernel: global ticket counter of the dynamic tile scheduler (nullptr = static round-robin)
   unsigned long long* stats;  // optional debug counters (cycles): [0] producer empty-wait, [1] mma full-wait,
                               // [2] mma tmem-empty wait, [3] epilogue tmem-full wait, [4] epilogue busy, [5] cta total
@@ -199,7 +200,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
   const int ncols = min(32, p.N - col0);  // multiple of 8 (host-checked)
 
   if constexpr (EPI == ABCGPT_EPI_BF16 || EPI == ABCGPT_EPI_GELU || EPI == ABCGPT_EPI_DGELU) {
-    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<long long>(row) * p.ldc +
+                       (p.head_stride ? (col0 >> 6) * p.head_stride + (col0 & 63) : col0);
     uint32_t pk[16];
     if constexpr (EPI == ABCGPT_EPI_DGELU) {
       // dH = bf16(acc) * gelu'(h): the reference's gelu_backward sees the bf16 dgrad output and the bf16 h
@@ -956,7 +958,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   p.M = M; p.N = N; p.K = K;
   p.num_m_blk = num_m_blk; p.num_n_blk = num_n_blk; p.num_k_blk = num_k_blk;
   p.splits = splits; p.kb_per_split = kb_per_split;
-  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.act_tanh = act_tanh; p.sched = (pair && !quad) ? sched_counter(stream) : nullptr; p.stats = g_gemm_stats; p.drop = make_drop(drop_p, drop_key);
+  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.act_tanh = act_tanh; p.head_stride = (epi == ABCGPT_EPI_BF16 && c2 == nullptr) ? ldc2 : 0; p.sched = (pair && !quad) ? sched_counter(stream) : nullptr; p.stats = g_gemm_stats; p.drop = make_drop(drop_p, drop_key);
   {
     const bool f32_out = (epi == ABCGPT_EPI_RESID || epi == ABCGPT_EPI_F32 || epi == ABCGPT_EPI_F32_RED);
     const long long cb = f32_out ? 4 : 2, ab = (epi == ABCGPT_EPI_RESID) ? 4 : 2;

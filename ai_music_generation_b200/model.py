@@ -694,8 +694,10 @@ class GPT(nn.Module):
         for li, lw in enumerate(layers):
             b = lambda name: None if lw[name] is None else lw[name][0]  # noqa: E731
             ops.layernorm_fwd(x, lw["ln_1.weight"][0], b("ln_1.bias"), st.ln, st.stat[0], st.stat[1])
-            qkv_t = st.cache[li][:, t * 3 * C:(t + 1) * 3 * C]  # the GEMM writes this position's row of the cache in place
-            ops.gemm(st.ln, lw["attn.c_attn.weight"][1], epilogue=ops.EPI_BF16, out=qkv_t, bias=b("attn.c_attn.bias"), tile_n=128)
+            # the GEMM writes this position's q | k | v straight into the head-major cache [B, 3H, Tmax, 64]
+            qkv_t = st.cache[li].view(B, 3 * H, st.Tmax, 64)[:, 0, t, :]
+            ops.gemm(st.ln, lw["attn.c_attn.weight"][1], epilogue=ops.EPI_BF16, out=qkv_t, bias=b("attn.c_attn.bias"), tile_n=128,
+                     head_stride=st.Tmax * 64)
             ops.attn_decode(st.cache[li], st.att, B, st.Tmax, t + 1, H)
             ops.gemm(st.att, lw["attn.c_proj.weight"][1], epilogue=ops.EPI_RESID, out=y, aux=x, bias=b("attn.c_proj.bias"),
                      tile_n=128)

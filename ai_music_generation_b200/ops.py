@@ -184,10 +184,12 @@ def _rowmajor_ld(t, name):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_BF16, out=None, out2=None, aux=None,
-         bias=None, tile_n=0, splits=0, drop_p=0.0, drop_key=0):
+         bias=None, tile_n=0, splits=0, drop_p=0.0, drop_key=0, head_stride=0):
     """out[M,N] = sum_k A[m,k] B[n,k] (bf16 in, fp32 accumulate on tcgen05).
 
-    a: [M,K] (a_mn=False) or stored [K,M] (a_mn=True); b: [N,K] or stored [K,N]."""
+    a: [M,K] (a_mn=False) or stored [K,M] (a_mn=True); b: [N,K] or stored [K,N].
+    head_stride (EPI_BF16 only): column c of output row m is stored at out[m, 0] + (c // 64) * head_stride + c % 64 — the
+    head-major KV cache of the decode path (`out` is then the [M, 64] view of the first head at the current position)."""
     _chk(a, torch.bfloat16, "gemm a")
     _chk(b, torch.bfloat16, "gemm b")
     lda, ldb = _rowmajor_ld(a, "gemm a"), _rowmajor_ld(b, "gemm b")
@@ -199,7 +201,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_B
     if Ka != Kb and (K is None):
         raise _C.AbcgptError(f"gemm: contraction mismatch {Ka} vs {Kb}")
     ldc = _rowmajor_ld(out, "gemm out")
-    ldc2 = _rowmajor_ld(out2, "gemm out2") if out2 is not None else 0
+    ldc2 = _rowmajor_ld(out2, "gemm out2") if out2 is not None else int(head_stride)
     ldaux = _rowmajor_ld(aux, "gemm aux") if aux is not None else 0
     if bias is not None:
         _chk(bias, torch.float32, "gemm bias")
