@@ -218,16 +218,24 @@ def main():
         opt.step()
         return loss
 
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    loss_ready = torch.cuda.Event()
+
     def step_e2e(i):
         hx, hy = host[i % n_host]
         x = hx.to(dev, non_blocking=True)
         y = hy.to(dev, non_blocking=True)
         _, loss = net(x, y)
+        # device -> host read of THIS step's loss, every step: the copy is enqueued right behind the forward (the value
+        # exists before the backward starts) and read at the end of the step, so the host never drains the whole step
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_ready.record()
         opt.zero_grad(set_to_none=True)
         loss.backward()
         model.clip_grad_norm_(1.0)
         opt.step()
-        return loss.item()  # device -> host read of the step's result
+        loss_ready.synchronize()
+        return float(loss_host[0])
 
     def barrier():
         if world > 1:
