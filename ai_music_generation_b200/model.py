@@ -332,7 +332,32 @@ class GPT(nn.Module):
             self._bufs[key] = _Buffers(self.config, B, T, self._arena["flat"].device, keep)
         return self._bufs[key]
 
+    # Programmatic dependent launch pays when the kernels of a step are short (baby GPT, 16 k tokens x 384: 3.02 -> 2.88 ms per
+    # step) and costs when every kernel fills the GPU for 25-400 us (GPT-2-small shape at 32 k tokens: -1.8 %), see DESIGN 4.5
+    _PDL_MAX_WORK = 8 * 1024 * 1024   # tokens x n_embd
+
     def _forward_plan(self, idx, targets, keep_activations, embeds=None, first=None, want_hidden=False):
+        src = idx if idx is not None else embeds
+        pdl = src.shape[0] * src.shape[1] * self.config.n_embd <= self._PDL_MAX_WORK
+        if not pdl:
+            return self._forward_plan_impl(idx, targets, keep_activations, embeds, first, want_hidden)
+        ops.set_pdl(True)
+        try:
+            return self._forward_plan_impl(idx, targets, keep_activations, embeds, first, want_hidden)
+        finally:
+            ops.set_pdl(False)
+
+    def _backward_plan(self, bufs, idx, targets, grad_loss, drop, d_hidden=None, mode=0):
+        pdl = bufs.B * bufs.T * self.config.n_embd <= self._PDL_MAX_WORK
+        if not pdl:
+            return self._backward_plan_impl(bufs, idx, targets, grad_loss, drop, d_hidden, mode)
+        ops.set_pdl(True)
+        try:
+            return self._backward_plan_impl(bufs, idx, targets, grad_loss, drop, d_hidden, mode)
+        finally:
+            ops.set_pdl(False)
+
+    def _forward_plan_impl(self, idx, targets, keep_activations, embeds=None, first=None, want_hidden=False):
         """embeds (fp32 [B,T,C]): the decoder is fed embeddings from another network (HF inputs_embeds) instead of token ids;
         first (fp32 [B,C]): token ids, but the first position's embedding is replaced (TunesFormer char decoder);
         want_hidden: also keep the fp32 ln_f output in bufs.hidden (HF last_hidden_state)."""
@@ -420,7 +445,7 @@ class GPT(nn.Module):
             bufs.plans[plan_key] = ops.end_record()
         return bufs
 
-    def _backward_plan(self, bufs, idx, targets, grad_loss, drop, d_hidden=None, mode=0):
+    def _backward_plan_impl(self, bufs, idx, targets, grad_loss, drop, d_hidden=None, mode=0):
         """mode 0: token ids in (the reference path); 1: inputs_embeds in (returns the fp32 gradient w.r.t. x[0], which is the
         gradient of the embeddings); 2: token ids with a replaced first embedding (`idx` must carry -1 at position 0 so that
         the wte gradient skips it; returns the same buffer, row 0 of every sequence is the gradient of `first`).
