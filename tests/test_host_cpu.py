@@ -142,3 +142,33 @@ def test_affine_plan_deltas_and_program_encoding():
     assert gemm[2 + 2 * 10: 4 + 2 * 10] == [9000 + 4608 * 2, 4608]              # the cache row pointer advances per position
     assert gemm[2 + 2 * 19] == struct.unpack("<q", struct.pack("<d", 0.0))[0]    # floats travel as double bit patterns
     assert ops.compile_affine([("x", 1, fake("abcgpt_unknown"), (1,), None)], [[]]) is None
+
+
+def test_dropout_numpy_twin_matches_the_kernel_header(tmp_path):
+    """csrc/dropout.cuh is __host__ __device__: compiled here with g++ (tests/helpers/dropout_host.cpp) it must produce exactly
+    the masks ai_music_generation_b200/dropout.py regenerates for the oracle — both generators (murmur lanes for the residual /
+    embedding sites, Weyl + folded multiply with 15-bit lanes and the carry-trick comparison for the attention site)."""
+    import shutil
+    import numpy as np
+    from ai_music_generation_b200 import dropout as D
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "dropout_host")
+    src = os.path.join(ROOT, "tests", "helpers", "dropout_host.cpp")
+    r = subprocess.run([gxx, "-O1", "-std=c++17", "-I", os.path.join(ROOT, "ai_music_generation_b200", "csrc"), src, "-o", exe],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for key, rows, cols, p in ((12345, 37, 70, 0.2), (0xDEADBEEF, 64, 129, 0.1), (7, 5, 33, 0.5)):
+        out = subprocess.run([exe, str(key), str(rows), str(cols), str(p)], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0
+        resid_s, attn_s = out.stdout.split("\n")[:2]
+        resid = np.frombuffer(resid_s.encode(), dtype=np.uint8).reshape(rows, cols) == ord("1")
+        attn = np.frombuffer(attn_s.encode(), dtype=np.uint8).reshape(rows, cols) == ord("1")
+        assert np.array_equal(resid, D.keep_mask(key, rows, cols, p))
+        # attention site: rows = (b*H + h)*T + q with B = H = 1, T = cols needs rows <= T; use the row counter directly
+        T = cols
+        host = D.attention_keep_mask(key, 1, (rows + T - 1) // T + 1, T, p).reshape(-1, T)[:rows]
+        assert np.array_equal(attn, host)
+        tol = 4.0 * (p * (1 - p) / (rows * cols)) ** 0.5
+        assert abs(attn.mean() - (1 - p)) < tol and abs(resid.mean() - (1 - p)) < tol
