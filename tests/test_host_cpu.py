@@ -172,3 +172,53 @@ def test_dropout_numpy_twin_matches_the_kernel_header(tmp_path):
         assert np.array_equal(attn, host)
         tol = 4.0 * (p * (1 - p) / (rows * cols)) ** 0.5
         assert abs(attn.mean() - (1 - p)) < tol and abs(resid.mean() - (1 - p)) < tol
+
+
+def test_dynamic_tile_scheduler_ticket_protocol_model():
+    """Model of the ticket protocol of gemm2_kernel's opt-in dynamic scheduler (csrc/gemm.cu): every pair processes its static
+    first item, then draws tickets (one held in flight); tickets < dyn_work map to item num_pairs + ticket, the first ticket
+    >= dyn_work ends the pair, which never draws again; the holder of ticket dyn_work + num_pairs - 1 resets the counter.
+    Under arbitrary interleavings (including pairs that start after all work is gone) every item is processed exactly
+    once, every pair draws exactly one end ticket and the counter is back at zero for the next launch."""
+    import random
+    rng = random.Random(0)
+    for trial in range(300):
+        num_pairs = rng.randint(1, 9)
+        total_work = rng.randint(num_pairs + 1, 60)
+        dyn_work = total_work - num_pairs
+        counter = [0]
+        resets = [0]
+        done_items = []
+        end_tickets = [0] * num_pairs
+        # per pair: pc 0 = not started; state = (pending ticket or None, drew_end)
+        pend = [None] * num_pairs
+        drew_end = [False] * num_pairs
+        phase = ["start"] * num_pairs   # start -> (draw pending, process static) -> loop: publish(pending), draw -> ...
+        active = list(range(num_pairs))
+        while active:
+            i = rng.choice(active)
+            if phase[i] == "start":
+                pend[i] = counter[0]; counter[0] += 1           # pending = draw()
+                done_items.append(i)                             # static first item
+                phase[i] = "loop"
+                continue
+            # end of a tile: publish(it + 1, pending); pending = draw()
+            w = pend[i]
+            nxt = None
+            if w is not None:
+                if w == dyn_work + num_pairs - 1:
+                    counter[0] = 0; resets[0] += 1
+                if w >= dyn_work:
+                    drew_end[i] = True; end_tickets[i] += 1
+                else:
+                    nxt = num_pairs + w
+            if not drew_end[i]:
+                pend[i] = counter[0]; counter[0] += 1
+            else:
+                pend[i] = None
+            if nxt is None:
+                active.remove(i)                                 # published -1: every role of this pair breaks
+            else:
+                done_items.append(nxt)
+        assert sorted(done_items) == list(range(total_work)), (trial, num_pairs, total_work)
+        assert end_tickets == [1] * num_pairs and resets[0] == 1 and counter[0] == 0
