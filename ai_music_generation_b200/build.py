@@ -17,8 +17,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libabcgpt.so")
-SOURCES = ["common.cu", "gemm.cu", "attn.cu", "layernorm.cu", "elementwise.cu", "microbench.cu", "api.cu"]
-HEADERS = ["common.h", "kernels.h", "ptx.cuh", "dropout.cuh", os.path.join("..", "..", "include", "abcgpt.h")]
+DEBUG_LIB_PATH = os.path.join(HERE, "libabcgpt_debug.so")  # product objects + instrumentation entry points (tools/ only)
+SOURCES = ["common.cu", "gemm.cu", "attn.cu", "layernorm.cu", "elementwise.cu", "sample.cu", "api.cu"]
+DEBUG_SOURCES = ["microbench.cu", "debug_api.cu"]  # include/abcgpt_debug.h; never linked into libabcgpt.so
+HEADERS = ["common.h", "kernels.h", "ptx.cuh", "dropout.cuh", os.path.join("..", "..", "include", "abcgpt.h"),
+           os.path.join("..", "..", "include", "abcgpt_debug.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,21 +41,22 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for name in SOURCES + HEADERS:
+    for name in SOURCES + DEBUG_SOURCES + HEADERS:
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile (if stale) and return the path of libabcgpt.so."""
-    stamp = os.path.join(OBJ_DIR, "stamp")
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """Compile (if stale) and return the path of libabcgpt.so (debug=True: also libabcgpt_debug.so, returns its path)."""
+    stamp = os.path.join(OBJ_DIR, "stamp_debug" if debug else "stamp")
+    target = DEBUG_LIB_PATH if debug else LIB_PATH
     digest = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
+    if not force and os.path.exists(target) and os.path.exists(stamp):
         with open(stamp) as f:
             if f.read().strip() == digest:
-                return LIB_PATH
+                return target
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
 
@@ -68,16 +72,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(res.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    with open(stamp, "w") as f:
-        f.write(digest)
-    return LIB_PATH
+    srcs = SOURCES + (DEBUG_SOURCES if debug else [])
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    # the product library never contains the instrumentation objects; the debug library is a superset
+    links = [(LIB_PATH, objs[:len(SOURCES)], "stamp")]
+    if debug:
+        links.append((DEBUG_LIB_PATH, objs, "stamp_debug"))
+    for path, members, stamp_name in links:
+        cmd = [nvcc, "-shared", "-o", path, *members, "-lcudart"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+        with open(os.path.join(OBJ_DIR, stamp_name), "w") as f:
+            f.write(digest)
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

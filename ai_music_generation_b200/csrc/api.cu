@@ -5,7 +5,6 @@
 #include <string.h>
 
 using namespace abcgpt;
-namespace abcgpt { extern unsigned long long* g_gemm_stats; extern long long* g_attn_trace; extern long long* g_attn_cta_trace; int tmem_ld_bench(long long*, int, int, int, cudaStream_t); int mma_bench(long long*, int, int, int, cudaStream_t); int mma2_bench(long long*, int, int, cudaStream_t); }
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
 
@@ -102,6 +101,10 @@ int abcgpt_colsum_bf16(const void* dy, int64_t ld, int M, int N, float* out, voi
 int abcgpt_argmax(const void* logits, int64_t ldl, int V, int64_t* out, int64_t out_stride, int B, void* stream) {
   return argmax_rows(logits, ldl, V, out, out_stride, B, S(stream));
 }
+int abcgpt_sample_topk(const void* logits, int64_t ldl, int V, float temperature, int top_k, const void* seed,
+                       int64_t counter, int64_t* out, int64_t out_stride, int B, void* stream) {
+  return sample_topk(logits, ldl, V, temperature, top_k, seed, counter, out, out_stride, B, S(stream));
+}
 
 /*
  * Replay of a recorded launch list with position-affine arguments (the decode loop of GPT.generate is launch-bound: ~90
@@ -150,6 +153,10 @@ int abcgpt_replay(const int64_t* prog, int64_t n_words, int64_t k) {
         if (nargs != 7) return fail(-1, "abcgpt_replay: argmax takes 7 arguments");
         rc = abcgpt_argmax(P_(0), a[1], I_(2), MP_(int64_t, 3), a[4], I_(5), P_(6));
         break;
+      case ABCGPT_FN_SAMPLE_TOPK:
+        if (nargs != 11) return fail(-1, "abcgpt_replay: sample_topk takes 11 arguments");
+        rc = abcgpt_sample_topk(P_(0), a[1], I_(2), abcgpt_word_f(a[3]), I_(4), P_(5), a[6], MP_(int64_t, 7), a[8], I_(9), P_(10));
+        break;
       default:
         return fail(-1, "abcgpt_replay: unknown function id %lld", (long long)fn);
     }
@@ -167,34 +174,6 @@ int abcgpt_replay(const int64_t* prog, int64_t n_words, int64_t k) {
  * kernels (a decoded token); default off. */
 int abcgpt_set_pdl(int on) {
   abcgpt::set_pdl(on != 0);
-  return 0;
-}
-
-/* debug: device pointer to 8 uint64 cycle counters filled by subsequent GEMM launches (NULL disables) */
-int abcgpt_debug_gemm_stats(void* device_counters) {
-  abcgpt::g_gemm_stats = reinterpret_cast<unsigned long long*>(device_counters);
-  return 0;
-}
-
-/* debug: 3 x (CTAs of one attention launch) x 4 int64 {start ns, end ns, SM id, steps}: forward, dK/dV, dQ kernels */
-int abcgpt_debug_attn_cta_trace(void* device_records) {
-  abcgpt::g_attn_cta_trace = reinterpret_cast<long long*>(device_records);
-  return 0;
-}
-
-/* debug: cycles of `iters` x (inflight x tcgen05.ld 32x32b.x32 + wait) on nwarps warps of one CTA; out[warp] */
-int abcgpt_debug_tmem_ld_bench(void* out, int iters, int nwarps, int inflight, void* stream) {
-  return abcgpt::tmem_ld_bench(reinterpret_cast<long long*>(out), iters, nwarps, inflight, S(stream));
-}
-
-/* debug: cycles of 4 x iters tcgen05.mma 128 x n x 16 (mode: A 0 smem K-major / 1 smem MN-major / 2 TMEM; +4 B MN-major) */
-int abcgpt_debug_mma_bench(void* out, int iters, int n, int mode, void* stream) {
-  if (mode < 0) return abcgpt::mma2_bench(reinterpret_cast<long long*>(out), iters, n, S(stream));  /* CTA pair, 256 x n x 16 */
-  return abcgpt::mma_bench(reinterpret_cast<long long*>(out), iters, n, mode, S(stream));
-}
-
-int abcgpt_debug_attn_trace(void* device_stamps) {
-  abcgpt::g_attn_trace = reinterpret_cast<long long*>(device_stamps);
   return 0;
 }
 

@@ -1,0 +1,48 @@
+// Debug / micro-benchmark entry points (include/abcgpt_debug.h).  NOT part of the product library: build.py links this file
+// and microbench.cu only into libabcgpt_debug.so, which the scripts under tools/ load explicitly.
+#include "common.h"
+#include "kernels.h"
+#include "../../include/abcgpt_debug.h"
+
+namespace abcgpt {
+extern unsigned long long* g_gemm_stats;
+extern long long* g_attn_trace;
+extern long long* g_attn_cta_trace;
+int tmem_ld_bench(long long*, int, int, int, cudaStream_t);
+int mma_bench(long long*, int, int, int, cudaStream_t);
+int mma2_bench(long long*, int, int, cudaStream_t);
+}  // namespace abcgpt
+
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+/* debug: device pointer to 8 uint64 cycle counters filled by subsequent GEMM launches (NULL disables) */
+int abcgpt_debug_gemm_stats(void* device_counters) {
+  abcgpt::g_gemm_stats = reinterpret_cast<unsigned long long*>(device_counters);
+  return 0;
+}
+
+/* debug: 3 x (CTAs of one attention launch) x 4 int64 {start ns, end ns, SM id, steps}: forward, dK/dV, dQ kernels */
+int abcgpt_debug_attn_cta_trace(void* device_records) {
+  abcgpt::g_attn_cta_trace = reinterpret_cast<long long*>(device_records);
+  return 0;
+}
+
+/* debug: cycles of `iters` x (inflight x tcgen05.ld 32x32b.x32 + wait) on nwarps warps of one CTA; out[warp] */
+int abcgpt_debug_tmem_ld_bench(void* out, int iters, int nwarps, int inflight, void* stream) {
+  return abcgpt::tmem_ld_bench(reinterpret_cast<long long*>(out), iters, nwarps, inflight, S(stream));
+}
+
+/* debug: cycles of 4 x iters tcgen05.mma 128 x n x 16 (mode: A 0 smem K-major / 1 smem MN-major / 2 TMEM; +4 B MN-major) */
+int abcgpt_debug_mma_bench(void* out, int iters, int n, int mode, void* stream) {
+  if (mode < 0) return abcgpt::mma2_bench(reinterpret_cast<long long*>(out), iters, n, S(stream));  /* CTA pair, 256 x n x 16 */
+  return abcgpt::mma_bench(reinterpret_cast<long long*>(out), iters, n, mode, S(stream));
+}
+
+int abcgpt_debug_attn_trace(void* device_stamps) {
+  abcgpt::g_attn_trace = reinterpret_cast<long long*>(device_stamps);
+  return 0;
+}
+
+}  // extern "C"

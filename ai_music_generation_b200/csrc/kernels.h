@@ -50,5 +50,7 @@ int sample_batch(const void* data, int token_bytes, long long n_tokens, const in
 int colsum_bf16(const void* dy, long long ld, int M, int N, float* out, cudaStream_t stream);
 int argmax_rows(const void* logits, long long ldl, int V, int64_t* out, long long out_stride, int B,
                 cudaStream_t stream);
+int sample_topk(const void* logits, long long ldl, int V, float temperature, int top_k, const void* seed, long long counter,
+                int64_t* out, long long out_stride, int B, cudaStream_t stream);
 
 }  // namespace abcgpt

@@ -16,8 +16,20 @@ import torch
 from . import ops
 
 
+def check_vocab(tokens, vocab_size, path):
+    """nn.Embedding raises on an id outside [0, V) (nanoGPT/model.py:177); the embedding kernel has no such check on its hot
+    path, so a token file that does not match meta.pkl's vocab_size (or uint16 data read as uint32) is rejected here, once,
+    when the file is loaded."""
+    if vocab_size is None or len(tokens) == 0:
+        return
+    top = int(tokens.max())
+    if top >= vocab_size:
+        raise ValueError(f"{path}: token id {top} is outside the vocabulary (vocab_size = {vocab_size}); "
+                         "wrong meta.pkl, or a token file of another width (uint16 / uint32)?")
+
+
 class DeviceTokenStream:
-    def __init__(self, data_dir, block_size, batch_size, device, wide_tokens=False):
+    def __init__(self, data_dir, block_size, batch_size, device, wide_tokens=False, vocab_size=None):
         self.T, self.B, self.device = block_size, batch_size, torch.device(device)
         self.dtype = np.uint32 if wide_tokens else np.uint16
         self.data = {}
@@ -25,6 +37,7 @@ class DeviceTokenStream:
             path = os.path.join(data_dir, f"{split}.bin")
             if os.path.exists(path):
                 host = np.fromfile(path, dtype=self.dtype)
+                check_vocab(host, vocab_size, path)
                 # torch has no uint32 tensors for arithmetic; the kernel only needs the bytes
                 view = host.view(np.int16 if self.dtype == np.uint16 else np.int32)
                 self.data[split] = torch.from_numpy(view).to(self.device)

@@ -82,13 +82,22 @@ class GradSync:
             self.finalize()
 
     def finalize(self):
+        """Releases the final bucket(s) and JOINS: the compute stream waits (device-side) for every outstanding collective.
+        After `loss.backward()` returns, anything the caller enqueues on the compute stream — the reference loop's stock
+        `torch.nn.utils.clip_grad_norm_(model.parameters(), ...)` (nanoGPT/train.py:350-352), `scaler.step`, a gradient
+        read — therefore sees fully reduced gradients, exactly as with torch DDP.  Nothing else is queued behind the
+        backward at this point, so the join costs no overlap."""
         for b in self._by_trigger.get(-1, ()):
             self._launch(b)
+        self._join()
 
-    def wait(self):
+    def _join(self):
         for w in self._pending:
             w.wait()  # NCCL: the current stream waits for the collective; the host does not block
         self._pending = []
+
+    def wait(self):
+        self._join()
         self.launched = []
 
 

@@ -119,6 +119,7 @@ class _Buffers:
         self.gl = e(1, dt=f32)
         self.hidden = None   # fp32 ln_f output, allocated on first use by the hierarchical (inputs_embeds) path
         self.plans = {}
+        self.gen = 0         # bumped by every forward into these buffers; an autograd node remembers the value it saw
         if keep_activations:
             self.dx = [e(M, C, dt=f32) for _ in range(2)]
             self.dxb = e(M, C)
@@ -153,6 +154,18 @@ class _DecodeState:
         self.affine = {}   # (flags) -> (t0, recorded plan at t0, per-launch argument deltas per position)
 
 
+def _check_generation(ctx):
+    """Activations live in per-(B, T) buffers that every training forward overwrites.  The reference (plain autograd) lets a
+    caller run two forwards and differentiate both afterwards (`(l1 + l2).backward()`); here that would differentiate loss 1
+    through forward 2's activations, so it raises instead of returning a wrong gradient.  forward/backward pairs in sequence —
+    the training loop, gradient accumulation — are unaffected."""
+    if ctx.gen != ctx.bufs.gen:
+        raise RuntimeError(
+            "GPT: backward() of a forward whose activations have been overwritten by a later forward of the same (batch, "
+            "sequence) shape.  Call loss.backward() before the next training forward (gradient accumulation does exactly "
+            "that), or run the extra forward under torch.no_grad().")
+
+
 class _GPTStep(torch.autograd.Function):
     """One autograd node for the whole network: forward launches the forward plan, backward the backward plan."""
 
@@ -162,13 +175,17 @@ class _GPTStep(torch.autograd.Function):
         if bufs.drop[0] == 0.0 and model._plan_cache_enabled:
             idx, targets = bufs.idx, bufs.tgt  # the plan staged the inputs into its static buffers
         ctx.model, ctx.bufs, ctx.idx, ctx.targets, ctx.drop = model, bufs, idx, targets, bufs.drop
+        ctx.gen = bufs.gen
         B, T = idx.shape
         logits = bufs.logits.view(B, T, -1)[:, :, : model.config.vocab_size]
         ctx.mark_non_differentiable(logits)
-        return logits, bufs.loss.view(())
+        # the loss is returned as its own 4-byte tensor (`losses.append(loss)` across steps keeps every value); the logits
+        # stay a view of the per-shape activation buffer: valid until the next forward of the same shape
+        return logits, bufs.loss.view(()).clone()
 
     @staticmethod
     def backward(ctx, _grad_logits, grad_loss):
+        _check_generation(ctx)
         ctx.model._backward_plan(ctx.bufs, ctx.idx, ctx.targets, grad_loss, ctx.drop)
         return None, None, None, None
 
@@ -188,6 +205,7 @@ class _GPTEmbedsStep(torch.autograd.Function):
             idx_b = idx.clone()
             idx_b[:, 0] = -1
         ctx.model, ctx.bufs, ctx.idx, ctx.targets, ctx.drop = model, bufs, idx_b, targets, bufs.drop
+        ctx.gen = bufs.gen
         ctx.want_hidden, ctx.mode, ctx.shape = want_hidden, mode, (B, T, C)
         loss = bufs.loss.view(()).clone() if targets is not None else torch.zeros((), device=x_in.device)
         hidden = bufs.hidden.view(B, T, C).clone() if want_hidden else torch.zeros(0, device=x_in.device)
@@ -196,6 +214,7 @@ class _GPTEmbedsStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, grad_hidden):
         B, T, C = ctx.shape
+        _check_generation(ctx)
         d_hidden = grad_hidden.reshape(B * T, C).float() if ctx.want_hidden and ctx.targets is None else None
         dx = ctx.model._backward_plan(ctx.bufs, ctx.idx, ctx.targets, grad_loss, ctx.drop, d_hidden=d_hidden, mode=ctx.mode)
         gx = dx.view(B, T, C).clone() if ctx.mode == 1 else dx.view(B, T, C)[:, 0, :].clone()
@@ -251,6 +270,13 @@ class GPT(nn.Module):
             offs.append(total)
             total += _round_up(p.numel(), 8)
         n_decay = sum(_round_up(p.numel(), 8) for _, p in params if p.dim() >= 2)
+        # the lm_head GEMMs read the vocabulary matrix as a [Vpad, C] operand (V rounded up to the 128-row tile): the rows past
+        # V must lie inside the arena (they produce the padding logits columns, which every consumer ignores)
+        cfg = self.config
+        vpad = _round_up(cfg.vocab_size, 128) if cfg.vocab_size <= 1024 else _round_up(cfg.vocab_size, 8)
+        for (_, p), o in zip(params, offs):
+            if p is self.lm_head.weight:
+                total = max(total, o + vpad * cfg.n_embd)
         flat = torch.zeros(total, device=device, dtype=torch.float32)
         for (_, p), o in zip(params, offs):
             flat[o:o + p.numel()].copy_(p.data.reshape(-1).to(torch.float32))
@@ -289,9 +315,19 @@ class GPT(nn.Module):
             self._shadow_fresh = False
         if a["grad"] is None:
             a["grad"] = torch.zeros(a["total"], device=a["flat"].device, dtype=torch.float32)
-        if not self._shadow_fresh:
+        # The GEMMs read the bf16 shadow.  FusedAdamW rewrites it itself; ANY other in-place edit of a parameter (p.data.copy_,
+        # re-initialisation, an EMA swap, a foreign optimizer) bumps that parameter's version counter, which is how a stale
+        # shadow is detected here (one recast launch).  Writes through `p.data` carry no version bump in PyTorch: after those
+        # call mark_weights_dirty().
+        ver = sum(p._version for p in a["params"]) + a["flat"]._version
+        if not self._shadow_fresh or ver != a.get("param_versions"):
             ops.cast_bf16(a["flat"], a["shadow"])
             self._shadow_fresh = True
+            a["param_versions"] = ver
+
+    def mark_weights_dirty(self):
+        """The fp32 parameters were changed behind the module's back: recast the bf16 GEMM-operand copy before the next use."""
+        self._shadow_fresh = False
 
     def _layer_tensors(self):
         """Per-layer (fp32 master, bf16 shadow, grad) views, cached per arena."""
@@ -381,6 +417,7 @@ class GPT(nn.Module):
         B, T = src.shape[0], src.shape[1]
         assert T <= cfg.block_size, f"Cannot forward sequence of length {T}, block size is only {cfg.block_size}"
         bufs = self._act_buffers(B, T, keep_activations)
+        bufs.gen += 1
         C, H, V = cfg.n_embd, cfg.n_head, cfg.vocab_size
         if idx is not None:
             idx = idx.contiguous()
@@ -561,7 +598,7 @@ class GPT(nn.Module):
             bufs = self._forward_plan(idx, targets, keep_activations=False)
         V = self.config.vocab_size
         if targets is not None:
-            return bufs.logits.view(B, T, -1)[:, :, :V], bufs.loss.view(())
+            return bufs.logits.view(B, T, -1)[:, :, :V], bufs.loss.view(()).clone()
         return bufs.last_logits[:, :V].unsqueeze(1), None
 
     def forward_hidden(self, inputs_embeds):
@@ -663,14 +700,13 @@ class GPT(nn.Module):
             forced = torch.zeros(total, B, device=idx.device, dtype=torch.int64)
             forced[:lmax] = idx[:, :lmax].t()
             st.col[:lmin].copy_(forced[:lmin])
-            greedy = top_k is not None and min(top_k, self.config.vocab_size) == 1
+            head = self._head(temperature, top_k)
+            self._reseed_sampler()
             last = total - 1
             ops.set_pdl(True)
             for t in range(last):
                 want = t >= lmin - 1
-                self._decode_step(st, t, want, greedy and want)
-                if want and not greedy:
-                    self._sample(st.logits, st.col[t + 1], 1, temperature, top_k)
+                self._decode_step(st, t, want, head if want else None)
                 if want and t + 1 < lmax:   # rows still inside their prompt take the prompt token, the others keep the sampled one
                     st.col[t + 1].copy_(torch.where(is_prompt[t + 1], forced[t + 1], st.col[t + 1]))
                 if stop_token is not None and t >= lmin and (t - lmin) % stop_check_every == stop_check_every - 1:
@@ -687,11 +723,13 @@ class GPT(nn.Module):
             self.train(was_training)
         return out
 
-    def _decode_step(self, st, t, want_logits, greedy):
+    def _decode_step(self, st, t, want_logits, head):
         """Position t of every sequence (tokens st.col[t]).  Appends this position's q|k|v to the cache and, if
-        want_logits, leaves the next-token logits in st.logits (greedy: also writes the argmax into st.col[t + 1]).
+        want_logits, leaves the next-token logits in st.logits and runs the sampling head, which writes token t + 1 of every
+        sequence into st.col[t + 1]: head = None (logits only), ("greedy",) = argmax, ("sample", temperature, top_k) = the
+        fused temperature / top-k / softmax / multinomial kernel (seeded per generate() call through self._sample_seed).
         Every argument is static per (t, flags), so the launch list is recorded once and replayed afterwards."""
-        flags = (want_logits, greedy, torch.cuda.current_stream().cuda_stream)
+        flags = (want_logits, head, torch.cuda.current_stream().cuda_stream)
         plan_key = (t,) + flags
         plan = st.plans.get(plan_key) if self._plan_cache_enabled else None
         if plan is not None:
@@ -735,8 +773,10 @@ class GPT(nn.Module):
             lnf_b = None if top["ln_f.bias"] is None else top["ln_f.bias"][0]
             ops.layernorm_fwd(x, top["ln_f.weight"][0], lnf_b, st.ln, st.stat[0], st.stat[1])
             ops.gemm(st.ln, top["wte"][1], N=st.Vpad, epilogue=ops.EPI_BF16, out=st.logits, tile_n=128)
-            if greedy:
+            if head is not None and head[0] == "greedy":
                 ops.argmax(st.logits, cfg.vocab_size, st.col[t + 1], out_stride=1)
+            elif head is not None:
+                ops.sample_topk(st.logits, cfg.vocab_size, st.col[t + 1], head[1], head[2], self._seed_buffer(), t)
         if self._plan_cache_enabled:
             plan = st.plans[plan_key] = ops.end_record()
             p1, p2 = st.plans.get((t - 1,) + flags), st.plans.get((t - 2,) + flags)
@@ -745,21 +785,33 @@ class GPT(nn.Module):
                 if d1 is not None and d1 == d2:
                     st.affine[flags] = (t, plan, d1, ops.compile_affine(plan, d1))
 
-    def _sample(self, logits_bf16, out_col, out_stride, temperature, top_k):
+    def _seed_buffer(self):
+        """uint64 device scalar read by the sampling kernel (its address is part of recorded launch lists)."""
+        dev = self._arena["flat"].device
+        buf = getattr(self, "_sample_seed", None)
+        if buf is None or buf.device != dev:
+            buf = torch.zeros(1, device=dev, dtype=torch.int64)
+            object.__setattr__(self, "_sample_seed", buf)
+        return buf
+
+    def _reseed_sampler(self):
+        """One draw from torch's CPU generator per generate() call: `torch.manual_seed(seed)` (sample.py:44) makes the sampled
+        tunes reproducible, and consecutive calls see different random streams."""
+        self._seed_buffer().fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
+
+    def _head(self, temperature, top_k):
         V = self.config.vocab_size
         if top_k is not None and min(top_k, V) == 1:
-            ops.argmax(logits_bf16, V, out_col, out_stride=out_stride)  # greedy: fused head, no host round trip
-            return
-        logits = logits_bf16[:, :V].float() / temperature
-        if top_k is not None:
-            v, _ = torch.topk(logits, min(top_k, V))
-            logits[logits < v[:, [-1]]] = -float("Inf")
-        probs = torch.softmax(logits, dim=-1)
-        nxt = torch.multinomial(probs, num_samples=1).view(-1)
-        if out_stride == 1:
-            out_col.copy_(nxt)
+            return ("greedy",)   # top_k = 1: the softmax over one surviving token is 1, the draw is its argmax
+        k = 0 if top_k is None else min(int(top_k), V)
+        return ("sample", float(temperature), 0 if k >= V else k)
+
+    def _sample(self, logits_bf16, out_col, out_stride, head, counter):
+        V = self.config.vocab_size
+        if head[0] == "greedy":
+            ops.argmax(logits_bf16, V, out_col, out_stride=out_stride)
         else:
-            out_col[:, 0].copy_(nxt)
+            ops.sample_topk(logits_bf16, V, out_col, head[1], head[2], self._seed_buffer(), counter, out_stride=out_stride)
 
     @torch.no_grad()
     def generate(self, idx, max_new_tokens, temperature=1.0, top_k=None, use_cache=True, stop_token=None, stop_check_every=64,
@@ -770,7 +822,9 @@ class GPT(nn.Module):
         While the context window does not slide (position < block_size) each new token costs ONE single-position step over
         a KV cache instead of the reference's full-context forward; absolute position embeddings make the cache invalid
         once the window slides, so from there on the context is recomputed per token exactly like the reference.
-        top_k == 1 (greedy) uses the fused argmax head writing straight into the pre-allocated token buffer.
+        The sampling head is one fused launch per token writing straight into the pre-allocated token buffer: argmax for
+        top_k == 1 (greedy), otherwise temperature / top-k crop / softmax / multinomial (abcgpt_sample_topk) with a Philox
+        stream seeded from torch's generator once per call.
 
         stop_token (extension, default off): sample.py cuts every generated tune at the first end-of-tune symbol
         (sample.py:163-165), so once EVERY sequence of the batch has produced it the remaining steps cannot change the
@@ -796,6 +850,8 @@ class GPT(nn.Module):
         self.eval()
         try:
             self._ensure_device_state()
+            head = self._head(temperature, top_k)
+            self._reseed_sampler()
             t = 0
             if use_cache and T0 <= bs:
                 key = ("decode", B, bs)
@@ -804,14 +860,11 @@ class GPT(nn.Module):
                 st = self._bufs[key]
                 last = min(total - 1, bs)   # positions 0 .. last-1 can be decoded with the cache
                 st.col[:T0].copy_(idx.t())
-                greedy = top_k is not None and min(top_k, self.config.vocab_size) == 1
                 stopped = False
                 ops.set_pdl(True)   # ~90 small dependent launches per token: overlap each launch / prologue with its predecessor
                 for t in range(last):
                     want = t >= T0 - 1
-                    self._decode_step(st, t, want, greedy and want)
-                    if want and not greedy:
-                        self._sample(st.logits, st.col[t + 1], 1, temperature, top_k)
+                    self._decode_step(st, t, want, head if want else None)
                     if stop_token is not None and t >= T0 and (t - T0) % stop_check_every == stop_check_every - 1:
                         if bool((st.col[T0:t + 2] == stop_token).any(dim=0).all()):
                             st.col[t + 2:last + 1].fill_(stop_token)
@@ -827,7 +880,7 @@ class GPT(nn.Module):
                 lo = max(0, pos + 1 - bs)
                 cond = out[:, lo:pos + 1].contiguous()
                 bufs = self._forward_plan(cond, None, keep_activations=False)
-                self._sample(bufs.last_logits, out[:, pos + 1:], out.stride(0), temperature, top_k)
+                self._sample(bufs.last_logits, out[:, pos + 1:], out.stride(0), head, pos)
         finally:
             ops.set_pdl(False)
             self.train(was_training)

@@ -320,6 +320,15 @@ def argmax(logits, V, out, out_stride=1):
     _call("argmax", 1, (B, V), _C.lib().abcgpt_argmax, logits.data_ptr(), ldl, V, out.data_ptr(), out_stride, B, _stream())
 
 
+def sample_topk(logits, V, out, temperature, top_k, seed, counter, out_stride=1):
+    """One multinomial draw per row from softmax(top-k(logits / temperature)) (include/abcgpt.h: abcgpt_sample_topk).
+    seed: uint64 device scalar (int64 tensor of one element); counter: the decode position."""
+    _chk(logits, torch.bfloat16, "sample logits")
+    B, ldl = logits.shape[0], logits.stride(0)
+    _call("sample_topk", 1, (B, V), _C.lib().abcgpt_sample_topk, logits.data_ptr(), ldl, V, float(temperature),
+          int(top_k) if top_k is not None else 0, seed.data_ptr(), int(counter), out.data_ptr(), out_stride, B, _stream())
+
+
 def colsum_bf16(dy, out):
     M, N = dy.shape
     _call("colsum_bf16", 1, (M, N), _C.lib().abcgpt_colsum_bf16, dy.data_ptr(), dy.stride(0), M, N, out.data_ptr(), _stream())

@@ -14,10 +14,10 @@ nanoGPT/bench.py:98-117).  Weak scaling: the per-GPU micro-batch is fixed as N g
            device -> host read of the loss inside every timed step.
 `roofline`, `kernel_breakdown` : per-kernel-family times from an instrumented pass (CUDA events on the launch
            stream around every C-ABI call), GEMM family against the measured cuBLAS bf16 peak.
-`cpu_baseline` / `--impl reference` : the CPU oracle port of the reference step (oracle/nanogpt_oracle.py, fp32,
-           all host threads) on a bounded sample of the same workload.  The Python reference itself cannot
-           travel to the GPU box (/root/reference does not exist there); the port is pinned to it by
-           tests/golden (see oracle/make_golden.py).
+`cpu_baseline` / `--impl reference` : the reference step on the host cores (fp32, all host threads, also under torchrun) on a
+           bounded sample of the same workload: the UNMODIFIED nanoGPT/model.py from the git-ignored byte-identical
+           copy baseline/_ref (tools/vendor_reference.py; kind "reference"), else the oracle port
+           (oracle/nanogpt_oracle.py, pinned to the reference by tests/golden; kind "port").
 """
 from __future__ import annotations
 
@@ -102,28 +102,72 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_oracle_tokens_per_s(wl, steps, warmup, batch=None):
+def host_threads():
+    """All host cores for the CPU arm.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU baseline
+    runs on rank 0 only, so it takes the whole machine back (otherwise the N > 1 baseline is a one-core number)."""
     import torch
-    from oracle import nanogpt_oracle as O
-    cfg = O.OracleConfig(**wl["cfg"])
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_reference_tokens_per_s(wl, steps, warmup, batch=None):
+    """One optimizer step of the reference on the host cores, fp32, on a bounded sample (cpu_batch sequences) of the workload.
+
+    kind "reference": the UNMODIFIED nanoGPT/model.py (byte-identical copy under baseline/_ref, tools/vendor_reference.py)
+    driven like nanoGPT/train.py:335-357 with device=cpu (forward, backward, stock clip_grad_norm_, torch AdamW from
+    configure_optimizers); kind "port": the oracle restatement (oracle/nanogpt_oracle.py), when the copy is absent.
+    Returns (tokens/s, s/step, batch, threads, kind)."""
+    import contextlib
+    import io
+    import torch
+    threads = host_threads()
     B = batch or wl["cpu_batch"]
-    T = cfg.block_size
-    torch.manual_seed(1337)
-    sd = {k: torch.randn(s) * 0.02 if len(s) > 1 else torch.ones(s) for k, s in O.param_shapes(cfg).items()}
+    T, V = wl["cfg"]["block_size"], wl["cfg"]["vocab_size"]
     g = torch.Generator().manual_seed(1234)
-    x = torch.randint(cfg.vocab_size, (B, T), generator=g)
-    y = torch.randint(cfg.vocab_size, (B, T), generator=g)
-    state, times = {}, []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        _, _, grads = O.loss_and_grads(sd, cfg, x, y)
-        c = O.clip_coef(O.grad_norm(grads), 1.0)
-        O.adamw_step(sd, {k: v * c for k, v in grads.items()}, state, lr=wl["lr"], betas=wl["betas"], weight_decay=0.1,
-                     step=it + 1)
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
+    x = torch.randint(V, (B, T), generator=g)
+    y = torch.randint(V, (B, T), generator=g)
+    times = []
+    from tools.vendor_reference import import_reference_model
+    ref = import_reference_model()
+    if ref is not None:
+        GPT, GPTConfig = ref
+        torch.manual_seed(1337)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = GPT(GPTConfig(**wl["cfg"]))
+            opt = model.configure_optimizers(0.1, wl["lr"], wl["betas"], "cpu")
+        model.train()
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            _, loss = model(x, y)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "reference"
+    else:
+        from oracle import nanogpt_oracle as O
+        cfg = O.OracleConfig(**wl["cfg"])
+        torch.manual_seed(1337)
+        sd = {k: torch.randn(s) * 0.02 if len(s) > 1 else torch.ones(s) for k, s in O.param_shapes(cfg).items()}
+        state = {}
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            _, _, grads = O.loss_and_grads(sd, cfg, x, y)
+            c = O.clip_coef(O.grad_norm(grads), 1.0)
+            O.adamw_step(sd, {k: v * c for k, v in grads.items()}, state, lr=wl["lr"], betas=wl["betas"], weight_decay=0.1,
+                         step=it + 1)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "port"
     dt = sum(times) / len(times)
-    return B * T / dt, dt, B, torch.get_num_threads()
+    return B * T / dt, dt, B, threads, kind
 
 
 def run_reference_arm(args, wl):
@@ -131,14 +175,15 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    tps, dt, B, threads = cpu_oracle_tokens_per_s(wl, steps, warmup)
-    sample = f"{steps} timed + {warmup} warm-up optimizer steps of {B}x{wl['cfg']['block_size']} tokens (fp32, CPU)"
+    tps, dt, B, threads, kind = cpu_reference_tokens_per_s(wl, steps, warmup)
+    what = "unmodified reference nanoGPT/model.py" if kind == "reference" else "oracle port"
+    sample = f"{steps} timed + {warmup} warm-up optimizer steps of {B}x{wl['cfg']['block_size']} tokens (fp32, CPU, {what})"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": wl["name"], "global_batch": B,
                                                         "seq_len": wl["cfg"]["block_size"], "parallelism": "cpu"},
-        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -342,9 +387,10 @@ def main():
         "kernel_breakdown": fam,
     }
     if not args.no_cpu_baseline:
-        tps, dt, cb, threads = cpu_oracle_tokens_per_s(wl, 2, 1)
-        out["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                               "sample": f"2 timed + 1 warm-up optimizer steps of {cb}x{T} tokens, fp32 oracle port"}
+        tps, dt, cb, threads, kind = cpu_reference_tokens_per_s(wl, 2, 1)
+        what = "unmodified reference nanoGPT/model.py" if kind == "reference" else "oracle port"
+        out["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": kind,
+                               "sample": f"2 timed + 1 warm-up optimizer steps of {cb}x{T} tokens, fp32, {what}"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,29 @@
+/*
+ * libabcgpt_debug — instrumentation and hardware micro-benchmarks used by the scripts under tools/ (tools/gemm_stats.py,
+ * tools/attn_trace.py, tools/attn_cta_timeline.py, tools/mma_bench.py, tools/tmem_bench.py).  These entry points are NOT in
+ * the product library libabcgpt.so: `python -m ai_music_generation_b200.build --debug` links them (csrc/debug_api.cu,
+ * csrc/microbench.cu) together with the product objects into libabcgpt_debug.so.
+ */
+#ifndef ABCGPT_DEBUG_H_
+#define ABCGPT_DEBUG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Debug aid: device pointer to 8 uint64 cycle counters accumulated by subsequent GEMM launches (NULL disables):
+ * [0] producer empty-wait [1] MMA full-wait [2] MMA tmem-empty wait [3] epilogue tmem-full wait [5] CTA total. */
+int abcgpt_debug_gemm_stats(void* device_counters);
+/* Debug aid: device pointer to int64[num_kv_tiles * 8]; one CTA of the next attention forward launches stamps clock64
+ * at its phase boundaries (NULL disables). */
+int abcgpt_debug_attn_trace(void* device_stamps);
+int abcgpt_debug_attn_cta_trace(void* device_records);
+int abcgpt_debug_mma_bench(void* out, int iters, int n, int mode, void* stream);
+int abcgpt_debug_tmem_ld_bench(void* out, int iters, int nwarps, int inflight, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABCGPT_DEBUG_H_ */

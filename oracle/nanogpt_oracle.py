@@ -282,6 +282,41 @@ def generate_greedy(sd, cfg: OracleConfig, idx, max_new_tokens: int, bf16: bool 
     return idx
 
 
+def sampling_probs(logits: torch.Tensor, temperature: float = 1.0, top_k: int | None = None) -> torch.Tensor:
+    """The distribution GPT.generate draws the next token from (model.py:318-324), for last-position logits [B, V] in the
+    dtype the model produced them in (bf16 under autocast: the division and the top-k comparison then run in bf16, the
+    softmax in fp32 as autocast does).  Returns fp64 probabilities."""
+    logits = logits / temperature
+    if top_k is not None:
+        v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
+        logits = logits.clone()
+        logits[logits < v[:, [-1]]] = -float("Inf")
+    return torch.softmax(logits.double(), dim=-1)
+
+
+def philox_uniform(seed: int, row: int, counter: int) -> float:
+    """Host twin of the uniform csrc/sample.cu draws for (seed, sequence, decode position): Philox4x32-10, key = seed,
+    counter = (row, counter lo, counter hi, 0x5A17), first output word >> 8 scaled to [0, 1)."""
+    M32 = 0xFFFFFFFF
+    k0, k1 = seed & M32, (seed >> 32) & M32
+    c0, c1, c2, c3 = row & M32, counter & M32, (counter >> 32) & M32, 0x5A17
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        hi0, lo0, hi1, lo1 = p0 >> 32, p0 & M32, p1 >> 32, p1 & M32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0, k1 = (k0 + 0x9E3779B9) & M32, (k1 + 0xBB67AE85) & M32
+    return (c0 >> 8) / 16777216.0
+
+
+def inverse_cdf_token(probs: torch.Tensor, u: float, eps: float = 0.0) -> set[int]:
+    """Token(s) the inverse-CDF draw may return for the uniform u: the smallest i with cumsum(p)_i > u.  eps > 0 widens the
+    comparison by the fp32 rounding of the device's running sum (returns every token whose CDF interval is within eps of u)."""
+    cdf = torch.cumsum(probs.double(), dim=-1)
+    lo = torch.cat((torch.zeros(1, dtype=torch.float64), cdf[:-1]))
+    ok = (probs > 0) & (lo - eps <= u) & (u < cdf + eps)
+    return set(torch.nonzero(ok).flatten().tolist())
+
+
 def num_params(cfg: OracleConfig, non_embedding: bool = True) -> int:
     n = sum(math.prod(s) for s in param_shapes(cfg).values())
     if non_embedding:

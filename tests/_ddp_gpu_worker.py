@@ -64,6 +64,82 @@ def tunesformer_case(rank, world, dev):
           f"{len(model.patch_level_decoder._grad_sync.buckets)}+{len(model.char_level_decoder._grad_sync.buckets)}", flush=True)
 
 
+def stock_train_loop_case(rank, world, dev):
+    """nanoGPT/train.py:335-357 verbatim (GradScaler(enabled=False), the STOCK torch.nn.utils.clip_grad_norm_ over
+    model.parameters(), scaler.step) with our DDP class in place of torch's: no explicit wait anywhere in the loop — the
+    backward itself must hand back fully reduced gradients (GradSync.finalize joins the compute stream).  Held to a
+    single-process run of the same loop over the concatenated batch, and replicas must stay bitwise identical."""
+    from ai_music_generation_b200 import evalloop
+    cfg = dict(block_size=128, vocab_size=95, n_layer=4, n_head=2, n_embd=128, dropout=0.0, bias=False)
+    torch.manual_seed(4242)   # same init everywhere
+    model = GPT(GPTConfig(**cfg)).to(dev).train()
+    ref = GPT(GPTConfig(**cfg)).to(dev).train()
+    ref.load_state_dict(model.state_dict())
+    raw_model = model
+    model = DDP(model, device_ids=[dev.index], bucket_mb=0.25)
+    g = torch.Generator().manual_seed(21)
+    B, accum, iters, grad_clip = 2, 2, 4, 1.0
+    data = [(torch.randint(95, (world * B, 128), generator=g), torch.randint(95, (world * B, 128), generator=g))
+            for _ in range(accum * iters + 1)]
+    ctx = torch.amp.autocast(device_type="cuda", dtype=torch.bfloat16)
+    results = []
+    for net, sl, is_ddp in ((model, slice(rank * B, (rank + 1) * B), True), (ref, slice(None), False)):
+        raw = raw_model if is_ddp else ref
+        scaler = torch.amp.GradScaler("cuda", enabled=False)
+        optimizer = raw.configure_optimizers(0.1, 1e-3, (0.9, 0.95), "cuda")
+        it = iter(data)
+
+        def get_batch(split):
+            x, y = next(it)
+            return x[sl].contiguous().to(dev), y[sl].contiguous().to(dev)
+
+        ddp, gradient_accumulation_steps = is_ddp, accum
+        norms = []
+        X, Y = get_batch("train")
+        for iter_num in range(iters):
+            for micro_step in range(gradient_accumulation_steps):
+                if ddp:
+                    net.require_backward_grad_sync = micro_step == gradient_accumulation_steps - 1
+                with ctx:
+                    logits, loss = net(X, Y)
+                    loss = loss / gradient_accumulation_steps
+                X, Y = get_batch("train")
+                scaler.scale(loss).backward()
+            if grad_clip != 0.0:
+                scaler.unscale_(optimizer)
+                norms.append(torch.nn.utils.clip_grad_norm_(net.parameters(), grad_clip).item())
+            scaler.step(optimizer)
+            scaler.update()
+            optimizer.zero_grad(set_to_none=True)
+        results.append((norms, raw._arena["flat"].clone()))
+    (n_ddp, p_ddp), (n_ref, p_ref) = results
+    for a, b in zip(n_ddp, n_ref):
+        assert abs(a - b) <= 2e-2 * b, (n_ddp, n_ref)
+    rel = ((p_ddp - p_ref).norm() / p_ref.norm()).item()
+    assert rel < 2e-3, rel
+    gathered = [torch.empty_like(p_ddp) for _ in range(world)]
+    dist.all_gather(gathered, p_ddp)
+    for other in gathered:
+        assert torch.equal(other, p_ddp), "replicas diverged under the stock loop"
+    # rank-sharded estimate_loss (train.py:231-244 / SURVEY 8f N4): world x ceil(n / world) batches, one all-reduce per split
+    evb = [(torch.randint(95, (2, 128), generator=g), torch.randint(95, (2, 128), generator=g)) for _ in range(4)]
+    cur = [0]
+
+    def eval_batch(split):   # rank r takes batches r, r + world, ...
+        x, y = evb[(rank + world * cur[0]) % 4]
+        cur[0] += 1
+        return x.to(dev), y.to(dev)
+
+    out = evalloop.estimate_loss(raw_model, eval_batch, 4, dev, shard=True, splits=("val",))
+    raw_model.eval()
+    with torch.no_grad():
+        want = sum(raw_model(x.to(dev), y.to(dev))[1].item() for x, y in evb) / 4
+    raw_model.train()
+    if world in (1, 2, 4):
+        assert abs(out["val"].item() - want) <= 1e-5, (out["val"].item(), want)
+    print(f"DDP_STOCK_LOOP_OK rank {rank} rel {rel:.2e} norms {n_ddp[0]:.4f}/{n_ref[0]:.4f} eval {out['val'].item():.5f}", flush=True)
+
+
 def main():
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
@@ -118,6 +194,7 @@ def main():
         assert torch.equal(other, flat), "ranks diverged"
     print(f"DDP_GPU_OK rank {rank} rel {rel:.2e} norm {norm.item():.4f} buckets {len(model._grad_sync.buckets)}", flush=True)
     tunesformer_case(rank, world, dev)
+    stock_train_loop_case(rank, world, dev)
     dist.destroy_process_group()
 
 

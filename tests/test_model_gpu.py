@@ -213,6 +213,7 @@ def test_ddp_two_gpus_nccl(cuda_device):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("DDP_GPU_OK") == 2
     assert r.stdout.count("DDP_TUNESFORMER_OK") == 2
+    assert r.stdout.count("DDP_STOCK_LOOP_OK") == 2
 
 
 def test_generate_kv_cache_equals_context_recompute_and_slides_like_reference(cuda_device):

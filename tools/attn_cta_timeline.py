@@ -4,6 +4,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ai_music_generation_b200 import _C, ops
+_C.use_debug_lib()  # instrumentation entry points live in libabcgpt_debug.so (include/abcgpt_debug.h)
 B, T, H = 32, 1024, 12
 C = H * 64
 qkv = torch.randn(B * T, 3 * C, device="cuda").bfloat16()

@@ -4,6 +4,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ai_music_generation_b200 import _C
+_C.use_debug_lib()  # instrumentation entry points live in libabcgpt_debug.so (include/abcgpt_debug.h)
 lib = _C.lib()
 out = torch.zeros(1, device="cuda", dtype=torch.int64)
 iters = 500

@@ -26,6 +26,8 @@ import torch
 import torch.distributed as dist
 
 from ai_music_generation_b200 import DDP, GPT, DeviceTokenStream, GPTConfig
+from ai_music_generation_b200 import evalloop
+from ai_music_generation_b200.data import check_vocab
 from configurator import load_settings
 
 DEFAULTS = dict(
@@ -46,9 +48,13 @@ class TokenStream:
     """`get_batch` of the reference (train.py:122-144): random windows of a memory-mapped token file, x and the shifted y
     as int64, pinned and copied asynchronously."""
 
-    def __init__(self, data_dir, block_size, batch_size, device, wide_tokens=False):
+    def __init__(self, data_dir, block_size, batch_size, device, wide_tokens=False, vocab_size=None):
         self.dir, self.T, self.B, self.device = data_dir, block_size, batch_size, device
         self.dtype = np.uint32 if wide_tokens else np.uint16
+        for name in ("train.bin", "val.bin"):  # one pass per file at start-up (see data.check_vocab)
+            path = os.path.join(data_dir, name)
+            if os.path.exists(path):
+                check_vocab(np.memmap(path, dtype=self.dtype, mode="r"), vocab_size, path)
 
     def get(self, split):
         data = np.memmap(os.path.join(self.dir, "train.bin" if split == "train" else "val.bin"), dtype=self.dtype, mode="r")
@@ -89,18 +95,24 @@ def main():
     torch.manual_seed(1337 + rank)
 
     data_dir = os.path.join("data", s["dataset"])
-    Loader = DeviceTokenStream if s["device_loader"] else TokenStream
-    stream = Loader(data_dir, s["block_size"], s["batch_size"], device,
-                    wide_tokens=s["out_dir"] == "out-irishman-whitespace")  # the reference's uint32 special case
     vocab = None
     meta_path = os.path.join(data_dir, "meta.pkl")
     if os.path.exists(meta_path):
         with open(meta_path, "rb") as f:
             vocab = pickle.load(f)["vocab_size"]
         print(f"found vocab_size = {vocab} (inside {meta_path})")
+    Loader = DeviceTokenStream if s["device_loader"] else TokenStream
+    stream = Loader(data_dir, s["block_size"], s["batch_size"], device,
+                    wide_tokens=s["out_dir"] == "out-irishman-whitespace",  # the reference's uint32 special case
+                    vocab_size=vocab)
 
+    # `model_args` goes into ckpt.pt and the reference's sample.py does GPTConfig(**checkpoint['model_args'])
+    # (nanoGPT/sample.py:59): the extra `activation` key is written only when it differs from the reference's GELU, so every
+    # checkpoint of a reference-shaped model loads in the reference unchanged
     model_args = dict(n_layer=s["n_layer"], n_head=s["n_head"], n_embd=s["n_embd"], block_size=s["block_size"],
-                      bias=s["bias"], vocab_size=None, dropout=s["dropout"], activation=s["activation"])
+                      bias=s["bias"], vocab_size=None, dropout=s["dropout"])
+    if s["activation"] != "gelu":
+        model_args["activation"] = s["activation"]
     iter_num, best_val = 0, 1e9
     checkpoint = None
     if s["init_from"] == "scratch":
@@ -112,7 +124,10 @@ def main():
         checkpoint = torch.load(os.path.join(s["out_dir"], "ckpt.pt"), map_location="cpu")
         for k in ("n_layer", "n_head", "n_embd", "block_size", "bias", "vocab_size"):
             model_args[k] = checkpoint["model_args"][k]
-        model_args["activation"] = checkpoint["model_args"].get("activation", "gelu")
+        if checkpoint["model_args"].get("activation", "gelu") != "gelu":
+            model_args["activation"] = checkpoint["model_args"]["activation"]
+        else:
+            model_args.pop("activation", None)
         model = GPT(GPTConfig(**model_args))
         sd = {k.removeprefix("_orig_mod."): v for k, v in checkpoint["model"].items()}
         model.load_state_dict(sd)
@@ -133,25 +148,8 @@ def main():
 
     shard_eval = ddp and s["sharded_eval"]
 
-    @torch.no_grad()
     def estimate_loss():
-        """Mean loss over eval_iters batches per split (train.py:231-244).  Losses accumulate on the device (one host sync per
-        split instead of one per batch); under DDP with sharded_eval every rank takes eval_iters / world of the batches."""
-        out = {}
-        raw_model.eval()
-        n_local = -(-s["eval_iters"] // world) if shard_eval else s["eval_iters"]
-        for split in ("train", "val"):
-            acc = torch.zeros(1, device=device)
-            for _ in range(n_local):
-                X, Y = stream.get(split)
-                _, loss = raw_model(X, Y)
-                acc += loss
-            if shard_eval:
-                dist.all_reduce(acc)
-                acc /= world
-            out[split] = (acc / n_local).cpu()[0]
-        raw_model.train()
-        return out
+        return evalloop.estimate_loss(raw_model, stream.get, s["eval_iters"], device, shard=shard_eval)
 
     log_path = os.path.join(s["out_dir"], "losses.jsonl")
     if master and not os.path.exists(log_path):
