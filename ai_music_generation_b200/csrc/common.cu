@@ -60,7 +60,7 @@ static CUtensorMapDataType dtype_of(int elem_bytes) {
 }
 
 static int encode_tmap_2d_uncached(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
-                                   uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+                                   uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
 // ---- descriptor cache ------------------------------------------------------------------------------------------------
 // A tensor map is a pure function of (pointer, element size, dims, pitch, box, swizzle) and costs a few microseconds of
@@ -96,13 +96,18 @@ constexpr size_t kTmapCacheMax = 16384;
 
 int encode_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
                    uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
-  const TmapKey key{ptr, inner, outer, row_bytes, box_inner, box_outer, elem_bytes, swizzle128 ? 1 : 0};
+  return encode_tmap_2d_sw(tm, ptr, elem_bytes, inner, outer, row_bytes, box_inner, box_outer, swizzle128 ? 128 : 0);
+}
+
+int encode_tmap_2d_sw(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                      uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  const TmapKey key{ptr, inner, outer, row_bytes, box_inner, box_outer, elem_bytes, swizzle_bytes};
   auto& cache = tmap_cache();
   if (auto it = cache.find(key); it != cache.end()) {
     *tm = it->second;
     return 0;
   }
-  const int rc = encode_tmap_2d_uncached(tm, ptr, elem_bytes, inner, outer, row_bytes, box_inner, box_outer, swizzle128);
+  const int rc = encode_tmap_2d_uncached(tm, ptr, elem_bytes, inner, outer, row_bytes, box_inner, box_outer, swizzle_bytes);
   if (rc == 0) {
     if (cache.size() >= kTmapCacheMax) cache.clear();
     cache.emplace(key, *tm);
@@ -111,20 +116,24 @@ int encode_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t in
 }
 
 static int encode_tmap_2d_uncached(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
-                                   uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+                                   uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-1, "TMA base pointer must be 16-byte aligned");
   if ((row_bytes & 15) != 0) return fail(-1, "TMA row pitch must be a multiple of 16 bytes (got %llu)",
                                          (unsigned long long)row_bytes);
-  if (swizzle128 && box_inner * elem_bytes != 128) return fail(-1, "swizzle128 needs a 128-byte inner box");
+  if (swizzle_bytes != 0 && swizzle_bytes != 64 && swizzle_bytes != 128) return fail(-1, "TMA swizzle must be 0, 64 or 128 bytes");
+  if (swizzle_bytes != 0 && box_inner * elem_bytes != static_cast<uint32_t>(swizzle_bytes))
+    return fail(-1, "a %d-byte swizzle needs a %d-byte inner box", swizzle_bytes, swizzle_bytes);
   if (box_inner > 256 || box_outer > 256) return fail(-1, "TMA box dims must be <= 256");
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, dtype_of(elem_bytes), 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(1000 + static_cast<int>(r), "cuTensorMapEncodeTiled(2d) failed with CUresult %d (inner=%llu outer=%llu "

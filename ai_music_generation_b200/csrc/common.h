@@ -68,6 +68,9 @@ inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t sm
 // 128-byte swizzle (box_inner * elem_bytes must be 128) or none.
 int encode_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
                    uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+// same with an explicit swizzle width: 0 (none), 64 or 128 bytes (= the inner box size in bytes)
+int encode_tmap_2d_sw(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                      uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 // 3D variant: [d2, d1, d0] with byte strides for d1 and d2.
 int encode_tmap_3d(CUtensorMap* tm, const void* ptr, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
                    uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,

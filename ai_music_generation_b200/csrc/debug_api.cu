@@ -11,6 +11,8 @@ extern long long* g_attn_cta_trace;
 int tmem_ld_bench(long long*, int, int, int, cudaStream_t);
 int mma_bench(long long*, int, int, int, cudaStream_t);
 int mma2_bench(long long*, int, int, cudaStream_t);
+int pair_probe(const void*, const void*, float*, int, cudaStream_t);
+int mufu_bench(long long*, float*, int, int, int, cudaStream_t);
 }  // namespace abcgpt
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
@@ -38,6 +40,16 @@ int abcgpt_debug_tmem_ld_bench(void* out, int iters, int nwarps, int inflight, v
 int abcgpt_debug_mma_bench(void* out, int iters, int n, int mode, void* stream) {
   if (mode < 0) return abcgpt::mma2_bench(reinterpret_cast<long long*>(out), iters, n, S(stream));  /* CTA pair, 256 x n x 16 */
   return abcgpt::mma_bench(reinterpret_cast<long long*>(out), iters, n, mode, S(stream));
+}
+
+/* debug: D[256,64] fp32 = A[256,64] bf16 x B[64,64] bf16 through one CTA-pair MMA chain (operand-format probe, tools/pair_probe.py) */
+int abcgpt_debug_pair_probe(const void* a, const void* b, void* d, int mode, void* stream) {
+  return abcgpt::pair_probe(a, b, reinterpret_cast<float*>(d), mode, S(stream));
+}
+
+/* debug: cycles of iters x 16 independent ex2 (mode 0), fma + ex2 (1) or an FMA-pipe exp2 (2) per thread, `warps` warps of one CTA; out[warp] */
+int abcgpt_debug_mufu_bench(void* out, void* sink, int iters, int warps, int mode, void* stream) {
+  return abcgpt::mufu_bench(reinterpret_cast<long long*>(out), reinterpret_cast<float*>(sink), iters, warps, mode, S(stream));
 }
 
 int abcgpt_debug_attn_trace(void* device_stamps) {

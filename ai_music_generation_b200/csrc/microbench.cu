@@ -188,3 +188,159 @@ int mma2_bench(long long* out, int iters, int n, cudaStream_t stream) {
   return launch_status("mma2_bench_kernel");
 }
 }  // namespace abcgpt
+
+// ---- debug probe: operand formats of the CTA-pair MMA used by the pair attention kernels (tools/pair_probe.py) ---------
+// D[256 x 64] = A[256 x 64] * B[64 x 64] with one tcgen05.mma.cta_group::2 chain (K = 64 = 4 instructions), A rows split over
+// the two CTAs, B split by N (32 columns per CTA).  mode bits:
+//   bit 0  B layout: 0 = MN-major [64 k x 32 n] slab, 64-byte rows, SWIZZLE_64B (TMA box 32 x 64)
+//                    1 = K-major  [32 n x 64 k] slab, 128-byte rows, SWIZZLE_128B (B given transposed: bt[n][k])
+//   bit 1  A source: 0 = shared memory (K-major SW128), 1 = tensor memory (bf16 pairs written by the CTA's threads)
+namespace abcgpt {
+namespace {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+pair_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __nv_bfloat16* __restrict__ a,
+                  float* __restrict__ d, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 32768);
+  uint64_t* done = full + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = ptx::uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool b_kmajor = mode & 1, a_tmem = mode & 2;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(full, 1);
+    ptx::mbar_init(done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(slot, 128);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ptx::uniform(*slot);
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  if (a_tmem) {  // A row (128 * rank + tid) as 32 packed bf16 pairs into TMEM columns [64, 96)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a + (128 * rank + threadIdx.x) * 64);
+    uint32_t w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = src[i];
+    ptx::tmem_st32(tmem_base + lane_off + 64, w);
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+  }
+  ptx::cluster_sync_all();  // both CTAs' TMEM operands are in place
+  ptx::tc_fence_after();
+  if (warp == 0) {
+    const bool issue = ptx::elect_one();
+    const uint32_t full_leader = ptx::mapa(ptx::smem_u32(full), 0);
+    const uint32_t b_bytes = b_kmajor ? 4096 : 4096;
+    if (rank == 0 && issue) ptx::mbar_expect_tx(full, 2 * (16384 + b_bytes));
+    if (issue) ptx::tma_load_2d_2sm(smem, &tmA, full_leader, 0, 128 * static_cast<int>(rank));
+    if (b_kmajor) {
+      if (issue) ptx::tma_load_2d_2sm(smem + 16384, &tmB, full_leader, 0, 32 * static_cast<int>(rank));   // rows [32 r, +32) of bt[n][k]
+    } else {
+      if (issue) ptx::tma_load_2d_2sm(smem + 16384, &tmB, full_leader, 32 * static_cast<int>(rank), 0);   // columns [32 r, +32) of b[k][n]
+    }
+    __syncwarp();
+  } else if (warp == 1 && rank == 0) {
+    const bool issue = ptx::elect_one();
+    ptx::mbar_wait(full, 0, 97);
+    ptx::tc_fence_after();
+    const uint32_t sA = ptx::smem_u32(smem), sB = sA + 16384;
+    const uint32_t idesc = ptx::umma_idesc_bf16(256, 64, 0, b_kmajor ? 0 : 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t adesc = ptx::umma_smem_desc(sA + k * 32, 0, 1024);
+      // MN-major SW64: 16 k-rows of 64 bytes per instruction = 1024 bytes; 8-row groups 512 bytes apart (SBO); one 32-wide MN atom
+      const uint64_t bdesc = b_kmajor ? ptx::umma_smem_desc(sB + k * 32, 0, 1024) : ptx::umma_smem_desc_lt(sB + k * 1024, 512, 512, 4);
+      if (issue) {
+        if (a_tmem) ptx::umma_ts_2sm(tmem_base, tmem_base + 64 + 8 * k, bdesc, idesc, k > 0);
+        else ptx::umma_ss_2sm(tmem_base, adesc, bdesc, idesc, k > 0);
+      }
+    }
+    if (issue) ptx::umma_commit_2sm(done, 0x3);
+    __syncwarp();
+  }
+  ptx::mbar_wait(done, 0, 96);
+  ptx::tc_fence_after();
+  uint32_t v0[32], v1[32];
+  ptx::tmem_ld32(tmem_base + lane_off, v0);
+  ptx::tmem_ld32(tmem_base + lane_off + 32, v1);
+  ptx::tmem_ld_wait();
+  float* o = d + (128 * rank + threadIdx.x) * 64;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(v0[i]); o[32 + i] = __uint_as_float(v1[i]); }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, 128);
+}
+}  // namespace
+int pair_probe(const void* a, const void* b, float* d, int mode, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = encode_tmap_2d(&tmA, a, 2, 64, 256, 128, 64, 128, true))) return rc;
+  if (mode & 1) rc = encode_tmap_2d(&tmB, b, 2, 64, 64, 128, 64, 32, true);          // bt[n][k]: rows-half, SW128
+  else rc = encode_tmap_2d_sw(&tmB, b, 2, 64, 64, 128, 32, 64, 64);                   // b[k][n]: columns-half, SW64
+  if (rc) return rc;
+  const int smem = 40 * 1024;
+  static bool done = false;
+  if (!done) {
+    ABCGPT_CUDA(cudaFuncSetAttribute(pair_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done = true;
+  }
+  pair_probe_kernel<<<2, 128, smem, stream>>>(tmA, tmB, reinterpret_cast<const __nv_bfloat16*>(a), d, mode);
+  return launch_status("pair_probe_kernel");
+}
+}  // namespace abcgpt
+
+// ---- debug micro-benchmark: MUFU.EX2 issue rate per scheduler (tools/mufu_bench.py) -------------------------------------
+namespace abcgpt {
+namespace {
+__global__ void __launch_bounds__(1024, 1) mufu_bench_kernel(long long* out, float* sink, int iters, int mode) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = -0.001f * static_cast<float>(threadIdx.x + i);
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (mode == 0) {
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+      } else if (mode == 1) {  // ex2 with an FMA in front (the softmax pattern)
+        x[i] = fmaf(x[i], 0.999f, -0.0001f);
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+      } else if (mode == 3) {  // packed half: two results per MUFU instruction?
+        uint32_t h = __float_as_uint(x[i]);
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h));
+        x[i] = __uint_as_float(h);
+      } else if (mode == 4) {
+        uint32_t h = __float_as_uint(x[i]);
+        asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(h));
+        x[i] = __uint_as_float(h);
+      } else {  // FMA-pipe only: Cody-Waite exp2 with a cubic (no MUFU)
+        const float t = x[i] + 12582912.f;
+        const float fr = x[i] - (t - 12582912.f);
+        float p = fmaf(fr, 0.0555041f, 0.2402265f);
+        p = fmaf(p, fr, 0.6931472f);
+        p = fmaf(p, fr, 1.0f);
+        x[i] = __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23)) * -0.5f;
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc += x[i];
+  if (acc == 1234.5f) sink[0] = acc;
+  if ((threadIdx.x & 31) == 0) out[blockIdx.x * 32 + (threadIdx.x >> 5)] = t1 - t0;
+}
+}  // namespace
+int mufu_bench(long long* out, float* sink, int iters, int warps, int mode, cudaStream_t stream) {
+  mufu_bench_kernel<<<1, warps * 32, 0, stream>>>(out, sink, iters, mode);
+  return launch_status("mufu_bench_kernel");
+}
+}  // namespace abcgpt

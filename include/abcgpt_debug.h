@@ -22,6 +22,11 @@ int abcgpt_debug_attn_trace(void* device_stamps);
 int abcgpt_debug_attn_cta_trace(void* device_records);
 int abcgpt_debug_mma_bench(void* out, int iters, int n, int mode, void* stream);
 int abcgpt_debug_tmem_ld_bench(void* out, int iters, int nwarps, int inflight, void* stream);
+/* Operand-format probe of the CTA-pair MMA: d[256,64] fp32 = a[256,64] bf16 x B; mode bit 0: b is B^T [n][k] (K-major halves) instead
+ * of B [k][n] (MN-major column halves, 64-byte swizzle); bit 1: A is staged through tensor memory. */
+/* MUFU.EX2 rate: cycles of iters x 16 independent ex2 per thread (mode 0), fma + ex2 (1), FMA-pipe-only exp2 (2); out[warp] */
+int abcgpt_debug_mufu_bench(void* out, void* sink, int iters, int warps, int mode, void* stream);
+int abcgpt_debug_pair_probe(const void* a, const void* b, void* d, int mode, void* stream);
 
 #ifdef __cplusplus
 }

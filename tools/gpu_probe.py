@@ -378,6 +378,10 @@ def build_cases():
     cases["attn_t64"] = lambda: case_attn("attn_t64", 3, 64, 2, True, timing=False)
     cases["attn_perf_cfg4_char"] = lambda: case_attn("attn_perf_cfg4_char", 8192, 32, 12, True)
     cases["attn_t200"] = lambda: case_attn("attn_t200", 2, 200, 2, True, timing=False)
+    # CTA-pair backward (T >= 256): tile counts that leave the pair's second tile partly / entirely past the sequence end
+    cases["attn_t300"] = lambda: case_attn("attn_t300", 2, 300, 2, True, timing=False)
+    cases["attn_t384"] = lambda: case_attn("attn_t384", 3, 384, 2, True, timing=False)
+    cases["attn_t512_many"] = lambda: case_attn("attn_t512_many", 40, 512, 4, True, timing=False)
     cases["attn_spike"] = lambda: case_attn("attn_spike", 2, 320, 2, True, timing=False, spike=True)
     cases["attn_perf_cfg2"] = lambda: case_attn("attn_perf_cfg2", 64, 256, 6, True)
     cases["attn_perf_cfg3"] = lambda: case_attn("attn_perf_cfg3", 32, 1024, 12, True)
