@@ -93,7 +93,8 @@ def use_debug_lib() -> None:
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        path = DEBUG_LIB_PATH if _use_debug else LIB_PATH
+        # ABCGPT_LIB: experiments only — load another build of the same ABI (A/B timing of two kernel variants on one box)
+        path = os.environ.get("ABCGPT_LIB") or (DEBUG_LIB_PATH if _use_debug else LIB_PATH)
         if not os.path.exists(path):
             raise AbcgptError(
                 f"{path} is missing: build it with `python -m ai_music_generation_b200.build` "

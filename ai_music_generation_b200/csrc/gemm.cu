@@ -272,6 +272,74 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
   }
 }
 
+// ---- bf16-output epilogues in two phases (pair kernel) --------------------------------------------------------------------
+// Phase 1 (pack_chunk) needs the accumulator: fp32 TMEM words (+ bias) -> packed bf16 pairs, 16 registers per 32 columns.
+// Phase 2 (finish_chunk) needs only those pairs: stores h, GELU and its store, or GELU' times the pre-activation.
+// Between the phases the warp hands its part of the TMEM accumulator back to the MMA issuer: the accumulator is released after
+// the two tcgen05.ld of a tile instead of after all of its arithmetic and global stores (the ncu source view of the
+// c_fc + GELU GEMM showed the MMA issuer starved for accumulator buffers while the epilogue warps sat in the long-scoreboard
+// stalls of their TMEM loads and in the MUFU chain), and both chunks' loads are in flight together.
+// MEASURED (same box, A/B of two builds through ABCGPT_LIB): c_fc + GELU 0.163 ms with this path against 0.155 ms with the
+// chunk-at-a-time epilogue, GELU' 0.179 vs 0.178, plain bf16 equal: 64 accumulator registers live at once leave the 96-register
+// budget of an 18-warp CTA no room (spills), and the accumulator hand-back was evidently not what the MMA issuer waits for.
+// Compiled only with -DABCGPT_GEMM_EPI_EARLY_RELEASE.
+[[maybe_unused]] __device__ __forceinline__ void pack_chunk(const GemmParams& p, int col0, const uint32_t (&r)[32], uint32_t (&pk)[16]) {
+  if (p.bias != nullptr && col0 < p.N) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void finish_chunk(const GemmParams& p, int row, int col0, uint32_t (&pk)[16], const AuxChunk<EPI>& aux) {
+  static_assert(EPI == ABCGPT_EPI_BF16 || EPI == ABCGPT_EPI_GELU || EPI == ABCGPT_EPI_DGELU, "bf16-output epilogues only");
+  if (row >= p.M || col0 >= p.N) return;
+  const int ncols = min(32, p.N - col0);  // multiple of 8 (host-checked)
+  __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<long long>(row) * p.ldc +
+                     (p.head_stride ? (col0 >> 6) * p.head_stride + (col0 & 63) : col0);
+  if constexpr (EPI == ABCGPT_EPI_DGELU) {
+    // dH = bf16(acc) * gelu'(h): the reference's gelu_backward sees the bf16 dgrad output and the bf16 h
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t hw = aux.v[i >> 3].v[i & 7];
+      const float2 hx = make_float2(ptx::bf16lo(hw), ptx::bf16hi(hw));
+      const float2 d = __fmul2_rn(make_float2(ptx::bf16lo(pk[i]), ptx::bf16hi(pk[i])), p.act_tanh ? gelu_tanh_bwd2(hx) : gelu_bwd2(hx));
+      pk[i] = ptx::pack_bf16x2(d.x, d.y);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) store_bf16x16(c, j, ncols, p.wide, pk + 8 * j);
+  if constexpr (EPI == ABCGPT_EPI_GELU) {
+    __nv_bfloat16* g = reinterpret_cast<__nv_bfloat16*>(p.c2) + static_cast<long long>(row) * p.ldc2 + col0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 hx = make_float2(ptx::bf16lo(pk[i]), ptx::bf16hi(pk[i]));  // GELU of the bf16 h
+      const float2 a = p.act_tanh ? gelu_tanh_fwd2(hx) : gelu_fwd2(hx);
+      pk[i] = ptx::pack_bf16x2(a.x, a.y);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) store_bf16x16(g, j, ncols, p.wide, pk + 8 * j);
+  }
+}
+
 __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, int tag, unsigned long long* stats, int slot,
                                            long long& acc) {
   if (stats == nullptr) {
@@ -533,6 +601,8 @@ struct Cfg2 {
 // CTA with the same role in the other pair: the L2 -> SM operand traffic per FLOP drops by a quarter.  That traffic is what
 // bounds this GEMM: a CTA pair issues 256x256x16 MMAs at the math rate (128 cycles, tools/mma_bench.py) but needs 64 B/clk
 // of operands per SM, 9.5 KB/clk chip-wide against ~6.3 KB/clk of L2 -> SM delivery: pairs alone top out at ~2/3 of peak.
+// 18 warps: ptxas caps the kernel at 96 registers per thread, and that IS the hardware limit (registers are allocated per warp
+// in units of 512: 112 per thread rounds to 4096 per warp, x 18 > 65 536 — a __maxnreg__(112) build fails to launch).
 template <bool A_MN, bool B_MN, int EPI, bool QUAD>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -756,22 +826,59 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int row = m0 + quarter * 32 + lane;
       const int col_base = n_blk * BN + half * COLS_PER_WARP;
       constexpr int NCH = COLS_PER_WARP / 32;
+      // auxiliary operands are requested before the accumulator wait (their DRAM latency hides behind the main loop), except
+      // for GELU': 96 registers do not hold two accumulator chunks AND two pre-activation chunks (420 bytes of spills); there
+      // they are requested right after the accumulator has been packed and released
+#ifdef ABCGPT_GEMM_EPI_EARLY_RELEASE
+      constexpr bool kAuxEarly = EPI != ABCGPT_EPI_DGELU;
+#else
+      constexpr bool kAuxEarly = true;
+#endif
       AuxChunk<EPI> aux[NCH];
+      if constexpr (kAuxEarly) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) load_aux<EPI>(aux[c], p, row, col_base + c * 32);
+        for (int c = 0; c < NCH; ++c) load_aux<EPI>(aux[c], p, row, col_base + c * 32);
+      }
       timed_wait(&tfull[as], aphase, 44, p.stats, 3, w0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
+#ifdef ABCGPT_GEMM_EPI_EARLY_RELEASE
+      if constexpr (EPI == ABCGPT_EPI_BF16 || EPI == ABCGPT_EPI_GELU || EPI == ABCGPT_EPI_DGELU) {
+#else
+      if constexpr (false) {
+#endif
+        // both chunks' TMEM loads in flight together, packed to bf16 at once, accumulator released BEFORE the arithmetic and
+        // the global stores (see pack_chunk)
+        uint32_t pk[NCH][16];
+        {
+          uint32_t r[NCH][32];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        epilogue_chunk<EPI>(p, row, col_base + c * 32, r, aux[c]);
+          for (int c = 0; c < NCH; ++c) ptx::tmem_ld32(taddr + c * 32, r[c]);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) pack_chunk(p, col_base + c * 32, r[c], pk[c]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[as]), crank & ~1u));
+        if constexpr (!kAuxEarly) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) load_aux<EPI>(aux[c], p, row, col_base + c * 32);
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) finish_chunk<EPI>(p, row, col_base + c * 32, pk[c], aux[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          epilogue_chunk<EPI>(p, row, col_base + c * 32, r, aux[c]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[as]), crank & ~1u));
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[as]), crank & ~1u));
     }
     if (p.stats && warp == 2 && lane == 0) {
       atomicAdd(&p.stats[3], static_cast<unsigned long long>(w0));
