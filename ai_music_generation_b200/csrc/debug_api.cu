@@ -13,6 +13,7 @@ int mma_bench(long long*, int, int, int, cudaStream_t);
 int mma2_bench(long long*, int, int, cudaStream_t);
 int pair_probe(const void*, const void*, float*, int, cudaStream_t);
 int mufu_bench(long long*, float*, int, int, int, cudaStream_t);
+int tmem_mma_bench(long long*, int, int, int, int, int, int, cudaStream_t);
 }  // namespace abcgpt
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
@@ -50,6 +51,12 @@ int abcgpt_debug_pair_probe(const void* a, const void* b, void* d, int mode, voi
 /* debug: cycles of iters x 16 independent ex2 (mode 0), fma + ex2 (1) or an FMA-pipe exp2 (2) per thread, `warps` warps of one CTA; out[warp] */
 int abcgpt_debug_mufu_bench(void* out, void* sink, int iters, int warps, int mode, void* stream) {
   return abcgpt::mufu_bench(reinterpret_cast<long long*>(out), reinterpret_cast<float*>(sink), iters, warps, mode, S(stream));
+}
+
+/* debug: tcgen05.ld cost while warp 1 issues 4 x mma_iters tcgen05.mma 128 x mma_n x 16 (mma_iters = 0: idle tensor core);
+ * out[0] = MMA chain cycles, out[2 + w] = cycles of `iters` x (inflight x ld (x16: 32x32b.x16, else .x32) + wait) on load warp w */
+int abcgpt_debug_tmem_mma_bench(void* out, int iters, int nwarps, int x16, int inflight, int mma_n, int mma_iters, void* stream) {
+  return abcgpt::tmem_mma_bench(reinterpret_cast<long long*>(out), iters, nwarps, x16, inflight, mma_n, mma_iters, S(stream));
 }
 
 int abcgpt_debug_attn_trace(void* device_stamps) {

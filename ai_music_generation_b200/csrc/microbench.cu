@@ -344,3 +344,95 @@ int mufu_bench(long long* out, float* sink, int iters, int warps, int mode, cuda
   return launch_status("mufu_bench_kernel");
 }
 }  // namespace abcgpt
+
+// ---- debug micro-benchmark: tcgen05.ld while the tensor core is busy (tools/tmem_mma_bench.py) --------------------------
+// One CTA: warp 1 issues a continuous chain of tcgen05.mma 128 x N x 16 (accumulator in TMEM columns [0, N)) while `nwarps`
+// other warps loop over tcgen05.ld 32x32b (x32 or x16, `inflight` loads per wait) on columns [256, 512).  Question: what does
+// a TMEM -> register load cost per warp, and how many bytes per clock does the SM deliver, when the MMA's own accumulator
+// traffic competes for tensor memory — the situation of every epilogue / softmax warp of the GEMM and attention kernels.
+namespace abcgpt {
+namespace {
+template <int N>
+__global__ void __launch_bounds__(576, 1) tmem_mma_bench_kernel(long long* out, int iters, int nwarps, int x16, int inflight, int mma_iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint32_t slot;
+  __shared__ uint64_t bar;
+  const int warp = ptx::uniform(threadIdx.x >> 5);
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(&slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ptx::uniform(slot);
+  if (warp == 1) {
+    const bool issue = ptx::elect_one();
+    const uint32_t sA = ptx::smem_u32(smem), sB = sA + 32768;
+    const uint32_t idesc = ptx::umma_idesc_bf16(128, N, 0, 0);
+    const long long t0 = clock64();
+    for (int i = 0; i < mma_iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t adesc = ptx::umma_smem_desc(sA + k * 32, 0, 1024);
+        const uint64_t bdesc = ptx::umma_smem_desc(sB + k * 32, 0, 1024);
+        if (issue) ptx::umma_ss(tmem_base, adesc, bdesc, idesc, 1);
+      }
+    }
+    if (issue) ptx::umma_commit(&bar);
+    ptx::mbar_wait(&bar, 0, 95);
+    const long long t1 = clock64();
+    if (issue) out[0] = t1 - t0;
+  } else if (warp >= 2 && warp < 2 + nwarps) {
+    const uint32_t base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 256 + ((warp - 2) >> 2) * 64;
+    uint32_t acc = 0;
+    uint32_t v[32], w[32];
+    uint32_t a16[16], b16[16];
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (x16) {
+        ptx::tmem_ld16(base, a16);
+        if (inflight >= 2) ptx::tmem_ld16(base + 16, b16);
+        ptx::tmem_ld_wait();
+        acc += a16[0] ^ a16[7] ^ a16[15];
+        if (inflight >= 2) acc += b16[0] ^ b16[7] ^ b16[15];
+      } else {
+        ptx::tmem_ld32(base, v);
+        if (inflight >= 2) ptx::tmem_ld32(base + 32, w);
+        ptx::tmem_ld_wait();
+        acc += v[0] ^ v[13] ^ v[31];
+        if (inflight >= 2) acc += w[0] ^ w[13] ^ w[31];
+      }
+    }
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) out[warp] = t1 - t0 + (acc == 0x12345u ? 1 : 0);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+}  // namespace
+// out[0] = cycles of the MMA chain (4 * mma_iters instructions), out[2 + w] = cycles of load warp w
+int tmem_mma_bench(long long* out, int iters, int nwarps, int x16, int inflight, int mma_n, int mma_iters, cudaStream_t stream) {
+  const int smem = 100 * 1024;
+  static bool done = false;
+  if (!done) {
+    ABCGPT_CUDA(cudaFuncSetAttribute(tmem_mma_bench_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ABCGPT_CUDA(cudaFuncSetAttribute(tmem_mma_bench_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ABCGPT_CUDA(cudaFuncSetAttribute(tmem_mma_bench_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done = true;
+  }
+  if (nwarps < 0 || nwarps > 16) return fail(-1, "tmem_mma_bench: 0..16 load warps");
+  if (mma_n == 64) tmem_mma_bench_kernel<64><<<1, 576, smem, stream>>>(out, iters, nwarps, x16, inflight, mma_iters);
+  else if (mma_n == 128) tmem_mma_bench_kernel<128><<<1, 576, smem, stream>>>(out, iters, nwarps, x16, inflight, mma_iters);
+  else tmem_mma_bench_kernel<256><<<1, 576, smem, stream>>>(out, iters, nwarps, x16, inflight, mma_iters);
+  return launch_status("tmem_mma_bench_kernel");
+}
+}  // namespace abcgpt

@@ -26,6 +26,8 @@ int abcgpt_debug_tmem_ld_bench(void* out, int iters, int nwarps, int inflight, v
  * of B [k][n] (MN-major column halves, 64-byte swizzle); bit 1: A is staged through tensor memory. */
 /* MUFU.EX2 rate: cycles of iters x 16 independent ex2 per thread (mode 0), fma + ex2 (1), FMA-pipe-only exp2 (2); out[warp] */
 int abcgpt_debug_mufu_bench(void* out, void* sink, int iters, int warps, int mode, void* stream);
+/* tcgen05.ld under tensor-core load: see csrc/microbench.cu (tools/tmem_mma_bench.py) */
+int abcgpt_debug_tmem_mma_bench(void* out, int iters, int nwarps, int x16, int inflight, int mma_n, int mma_iters, void* stream);
 int abcgpt_debug_pair_probe(const void* a, const void* b, void* d, int mode, void* stream);
 
 #ifdef __cplusplus

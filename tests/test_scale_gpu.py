@@ -66,9 +66,12 @@ def test_gpt2_small_shape_training_step_matches_reference(cuda_device):
         got = gt.flatten()[idx]
         want = torch.tensor(rec["grad_samples"][n])
         rms = ref_norm / (gt.numel() ** 0.5)
-        # an element deviates like the tensor's relative L2 error times its RMS (x4: eight samples, heavy-tailed)
+        # an element deviates like the tensor's relative L2 error times its magnitude scale (x4: eight samples, heavy-tailed;
+        # the scale is the larger of the tensor's RMS and the largest pinned element, since gradient rows of frequent tokens /
+        # early positions sit far above the RMS and their rounding noise scales with them)
         dev = (got - want).abs().max().item()
-        assert dev <= 4.0 * rel_allow * rms + 1e-9, (n, dev, rms, rel_allow)
+        scale = max(rms, want.abs().max().item())
+        assert dev <= 4.0 * rel_allow * scale + 1e-9, (n, dev, rms, scale, rel_allow)
         worst = max(worst, dev / (rms + 1e-30))
     total = model.clip_grad_norm_(1.0)
     assert total.item() == pytest.approx(rec["grad_norm_total"], rel=1.5 * abs(yard["grad_norm_total"] / rec["grad_norm_total"] - 1) + 5e-3)
