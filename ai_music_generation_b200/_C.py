@@ -35,6 +35,7 @@ _SIGNATURES = {
     "abcgpt_pos_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "abcgpt_onehot_bf16": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "abcgpt_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "abcgpt_layernorm_fwd_resid": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_uint32, _P]),
     "abcgpt_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_uint32, _P]),
     "abcgpt_attn_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, c_uint32, _P]),
     "abcgpt_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_uint32, _P]),

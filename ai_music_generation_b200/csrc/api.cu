@@ -48,6 +48,11 @@ int abcgpt_layernorm_fwd(const float* x, const float* weight, const float* bias,
                          float* mean, float* rstd, int M, int C, void* stream) {
   return layernorm_fwd(x, weight, bias, y_bf16, y_f32, mean, rstd, M, C, S(stream));
 }
+int abcgpt_layernorm_fwd_resid(const float* x_in, const void* branch_bf16, float* x_out, const float* weight, const float* bias,
+                               void* y_bf16, float* mean, float* rstd, int M, int C, float dropout_p, uint32_t dropout_key,
+                               void* stream) {
+  return layernorm_fwd_resid(x_in, branch_bf16, x_out, weight, bias, y_bf16, mean, rstd, M, C, dropout_p, dropout_key, S(stream));
+}
 int abcgpt_layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean,
                          const float* rstd, const float* dresid_in, float* dx_out, void* dx_bf16, float* dweight,
                          float* dbias, int M, int C, float dropout_p, uint32_t dropout_key, void* stream) {

@@ -66,7 +66,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int nqt = (T + 127) / 128;
   const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
   int total_steps = 0;
-#define ATTN_STAMP(k) do { if (tr && item_k == 0 && j < 16) trace[j * 8 + (k)] = clock64(); } while (0)
+// debug stamps (abcgpt_debug_attn_trace): the first 120 steps of CTA 0's row-0 thread; slot 5 = item ordinal, 6 = tile, 7 = globaltimer
+#define ATTN_STAMP(k) do { if (tr && gt < 120) { trace[gt * 8 + (k)] = clock64(); if ((k) == 0) { trace[gt * 8 + 5] = item_k; trace[gt * 8 + 6] = j; trace[gt * 8 + 7] = globaltimer_ns(); } } } while (0)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);

@@ -23,6 +23,9 @@ int onehot_bf16(const int64_t* tok, void* out, int M, int S, int V, cudaStream_t
 
 int layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* y_f32, float* mean,
                   float* rstd, int M, int C, cudaStream_t stream);
+int layernorm_fwd_resid(const float* x_in, const void* branch_bf16, float* x_out, const float* weight, const float* bias,
+                        void* y_bf16, float* mean, float* rstd, int M, int C, float drop_p, uint32_t drop_key,
+                        cudaStream_t stream);
 int layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean, const float* rstd,
                   const float* dresid_in, float* dx_out, void* dx_bf16, float* dweight, float* dbias, int M, int C,
                   float drop_p, uint32_t drop_key, cudaStream_t stream);

@@ -20,11 +20,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <int NV>  // NV float4 per lane: C <= NV*128
+// ADD: the residual add of the block is fused in front of the normalisation (model.py:103 `x = x + self.attn(...)` followed
+// by :104 `self.ln_2(x)`): x_sum = x + [dropout](branch), branch = the bf16 output of the preceding Linear; x_sum is written
+// (fp32 residual stream) and normalised in the same pass.  Same arithmetic as the RESID epilogue of the GEMM (csrc/gemm.cu):
+// the bf16 Linear output is added into the fp32 stream, the residual-branch dropout masks / rescales / re-rounds it first.
+template <int NV, bool ADD>  // NV float4 per lane: C <= NV*128
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
               __nv_bfloat16* __restrict__ y, float* __restrict__ yf, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, int M, int C) {
+              float* __restrict__ rstd_out, int M, int C, const __nv_bfloat16* __restrict__ branch,
+              float* __restrict__ xsum, DropCfg drop) {
   ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
   ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -34,11 +39,39 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
   float4 v[NV];
   float s = 0.f;
+  if constexpr (ADD) {
+    const uint2* br = reinterpret_cast<const uint2*>(branch + static_cast<long long>(row) * C);
+    float4* xs = reinterpret_cast<float4*>(xsum + static_cast<long long>(row) * C);
+    uint2 bv[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int idx = lane + 32 * i;
-    v[i] = (idx < nvec) ? __ldg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int i = 0; i < NV; ++i) {  // the whole row of both operands is requested up front
+      const int idx = lane + 32 * i;
+      v[i] = (idx < nvec) ? __ldg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      bv[i] = (idx < nvec) ? __ldg(br + idx) : make_uint2(0u, 0u);
+    }
+    const uint32_t rk = drop_row_key(drop.key, static_cast<uint32_t>(row));
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + 32 * i;
+      float y0 = ptx::bf16lo(bv[i].x), y1 = ptx::bf16hi(bv[i].x), y2 = ptx::bf16lo(bv[i].y), y3 = ptx::bf16hi(bv[i].y);
+      if (drop.thr16 != 0) {  // bf16 dropout like nn.Dropout on the bf16 Linear output: scale, round, or zero
+        const uint32_t b0 = drop_pair_bits(rk, 2 * idx), b1 = drop_pair_bits(rk, 2 * idx + 1);
+        y0 = drop_keep_lo(b0, drop.thr16) ? ptx::bf16_round(y0 * drop.inv_keep) : 0.f;
+        y1 = drop_keep_hi(b0, drop.thr16) ? ptx::bf16_round(y1 * drop.inv_keep) : 0.f;
+        y2 = drop_keep_lo(b1, drop.thr16) ? ptx::bf16_round(y2 * drop.inv_keep) : 0.f;
+        y3 = drop_keep_hi(b1, drop.thr16) ? ptx::bf16_round(y3 * drop.inv_keep) : 0.f;
+      }
+      v[i].x += y0; v[i].y += y1; v[i].z += y2; v[i].w += y3;
+      if (idx < nvec) xs[idx] = v[i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + 32 * i;
+      v[i] = (idx < nvec) ? __ldg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
   }
   const float mean = warp_sum(s) / static_cast<float>(C);
   float ss = 0.f;
@@ -218,9 +251,25 @@ int layernorm_fwd(const float* x, const float* weight, const float* bias, void* 
   ABCGPT_CHECK_ARG(x && weight && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
   const int nv = (C + 127) / 128;
   const int grid = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  LN_DISPATCH(nv, (launch_k(ln_fwd_kernel<NV>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream, 
-                      x, weight, bias, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, C)));
+  LN_DISPATCH(nv, (launch_k(ln_fwd_kernel<NV, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
+                      x, weight, bias, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, C,
+                      static_cast<const __nv_bfloat16*>(nullptr), static_cast<float*>(nullptr), DropCfg{})));
   return launch_status("ln_fwd_kernel");
+}
+
+int layernorm_fwd_resid(const float* x_in, const void* branch_bf16, float* x_out, const float* weight, const float* bias,
+                        void* y_bf16, float* mean, float* rstd, int M, int C, float drop_p, uint32_t drop_key,
+                        cudaStream_t stream) {
+  ABCGPT_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0 && C <= 2048, "layernorm: need C %% 4 == 0 and C <= 2048 (got %d)", C);
+  ABCGPT_CHECK_ARG(x_in && branch_bf16 && x_out && weight && y_bf16, "layernorm_fwd_resid: null pointer");
+  ABCGPT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "layernorm_fwd_resid: dropout probability must be in [0, 1)");
+  const DropCfg drop = make_drop(drop_p, drop_key);
+  const int nv = (C + 127) / 128;
+  const int grid = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  LN_DISPATCH(nv, (launch_k(ln_fwd_kernel<NV, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
+                      x_in, weight, bias, reinterpret_cast<__nv_bfloat16*>(y_bf16), static_cast<float*>(nullptr), mean, rstd, M, C,
+                      reinterpret_cast<const __nv_bfloat16*>(branch_bf16), x_out, drop)));
+  return launch_status("ln_fwd_kernel (residual add)");
 }
 
 int layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean, const float* rstd,

@@ -261,6 +261,16 @@ def layernorm_fwd(x, weight, bias, y_bf16, mean, rstd, y_f32=None):
           _ptr(y_bf16), _ptr(y_f32), _ptr(mean), _ptr(rstd), M, C, _stream())
 
 
+def layernorm_fwd_resid(x_in, branch_bf16, x_out, weight, bias, y_bf16, mean, rstd, drop_p=0.0, drop_key=0):
+    """x_out = x_in + [dropout](branch), y = LN(x_out) in one pass (include/abcgpt.h: abcgpt_layernorm_fwd_resid)."""
+    _chk(x_in, torch.float32, "layernorm x_in")
+    _chk(branch_bf16, torch.bfloat16, "layernorm branch")
+    M, C = x_in.shape
+    _call("layernorm_fwd_resid", 1, (M, C), _C.lib().abcgpt_layernorm_fwd_resid, x_in.data_ptr(), branch_bf16.data_ptr(),
+          x_out.data_ptr(), weight.data_ptr(), _ptr(bias), y_bf16.data_ptr(), _ptr(mean), _ptr(rstd), M, C, drop_p, drop_key,
+          _stream())
+
+
 def layernorm_bwd(dy_bf16, x, weight, mean, rstd, dresid_in, dx_out, dx_bf16, dweight, dbias, drop_p=0.0, drop_key=0):
     M, C = x.shape
     _call("layernorm_bwd", 1, (M, C), _C.lib().abcgpt_layernorm_bwd, dy_bf16.data_ptr(), x.data_ptr(), weight.data_ptr(),

@@ -11,19 +11,21 @@ o = torch.empty(B * T, C, device="cuda", dtype=torch.bfloat16)
 lse = torch.empty(B, H, T, device="cuda")
 for _ in range(3):
     ops.attn_fwd(qkv, o, lse, B, T, H)
-tr = torch.zeros(16 * 8, device="cuda", dtype=torch.int64)
+tr = torch.zeros(128 * 8, device="cuda", dtype=torch.int64)
 _C.lib().abcgpt_debug_attn_trace(tr.data_ptr())
 ops.attn_fwd(qkv, o, lse, B, T, H)
 torch.cuda.synchronize()
 _C.lib().abcgpt_debug_attn_trace(0)
 
-n = 16
-print("tile: wait_S  compute  wait_Pbuf  store+arrive | total")
 t = tr.view(-1, 8).cpu()
+n = int((t[:, 4] > 0).sum().item())
+print("step item tile: wait_S  compute  wait_Pbuf  store+arrive | total | since previous step start")
 for j in range(n):
     r = t[j]
-    print(j, (r[1] - r[0]).item(), (r[2] - r[1]).item(), (r[3] - r[2]).item(), (r[4] - r[3]).item(), "|", (r[4] - r[0]).item())
-print("whole CTA:", (t[n - 1][4] - t[0][0]).item(), "cycles")
+    print(j, int(r[5]), int(r[6]), ":", (r[1] - r[0]).item(), (r[2] - r[1]).item(), (r[3] - r[2]).item(), (r[4] - r[3]).item(), "|", (r[4] - r[0]).item(),
+          "|", (r[0] - t[j - 1][0]).item() if j else 0)
+cyc, ns = (t[n - 1][0] - t[0][0]).item(), (t[n - 1][7] - t[0][7]).item()
+print(f"forward CTA 0: {n} steps, {cyc} cycles, {ns} ns -> {cyc / max(ns, 1) * 1e3:.0f} MHz effective SM clock, {cyc / (n - 1):.0f} cycles per step")
 
 # backward kernels: stamps of group 0's first 64 own steps (across items): dq at [0,512), dkv at [512,1024)
 do = torch.randn(B * T, C, device="cuda").bfloat16()

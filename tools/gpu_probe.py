@@ -240,6 +240,29 @@ def case_layernorm(name, M, C, bias):
     return res
 
 
+def case_layernorm_resid(name, M, C, bias):
+    """x_out = x_in + branch (bf16), y = LN(x_out) in one pass; exact fp32 add, LN against torch."""
+    import torch
+    from ai_music_generation_b200 import ops
+    torch.manual_seed(1)
+    dev = "cuda"
+    x = torch.randn(M, C, device=dev) * 2 + 0.5
+    br = torch.randn(M, C, device=dev).bfloat16()
+    w = torch.randn(C, device=dev)
+    b = torch.randn(C, device=dev) if bias else None
+    xo = torch.zeros(M, C, device=dev)
+    y = torch.zeros(M, C, device=dev, dtype=torch.bfloat16)
+    mean, rstd = torch.zeros(M, device=dev), torch.zeros(M, device=dev)
+    ops.layernorm_fwd_resid(x, br, xo, w, b, y, mean, rstd)
+    xs = x + br.float()
+    yr = torch.nn.functional.layer_norm(xs, (C,), w, b, 1e-5)
+    res = {"case": name, "errs": [_err(xo, xs), _err(y, yr), _err(mean, xs.mean(-1)), _err(rstd, (xs.var(-1, unbiased=False) + 1e-5).rsqrt())]}
+    res["ok"] = bool(torch.equal(xo, xs)) and res["errs"][1]["max_abs"] < 0.05 and res["errs"][2]["max_abs"] < 1e-5 and res["errs"][3]["rel_l2"] < 1e-5
+    ms = _timeit(lambda: ops.layernorm_fwd_resid(x, br, xo, w, b, y, mean, rstd))
+    res["fwd_ms"], res["fwd_gbs"] = ms, (4 + 2 + 4 + 2) * M * C / ms / 1e6
+    return res
+
+
 def case_ce(name, M, V, ldl):
     import torch
     from ai_music_generation_b200 import ops
@@ -390,6 +413,8 @@ def build_cases():
     cases["ln_768"] = lambda: case_layernorm("ln_768", 32768, 768, False)
     cases["ln_768_bias"] = lambda: case_layernorm("ln_768_bias", 4096, 768, True)
     cases["ln_1000"] = lambda: case_layernorm("ln_1000", 1000, 1000, True)
+    cases["ln_resid_768"] = lambda: case_layernorm_resid("ln_resid_768", 32768, 768, False)
+    cases["ln_resid_1000_bias"] = lambda: case_layernorm_resid("ln_resid_1000_bias", 1000, 1000, True)
     cases["ce_95"] = lambda: case_ce("ce_95", 32768, 95, 128)
     cases["ce_50304"] = lambda: case_ce("ce_50304", 512, 50304, 50304)
     cases["adamw"] = lambda: case_adamw("adamw", 85813248 // 8 + 3)
