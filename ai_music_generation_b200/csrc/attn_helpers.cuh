@@ -47,7 +47,11 @@ __device__ __forceinline__ float ex2(float x) {
 // 0.302 ms per layer): the ncu source view of the same run shows the compute warps 36 % of their time in the wait for the next
 // score tile, i.e. the step pipeline (three TMEM score buffers, MMA -> softmax -> MMA round trip) is the limit, not the MUFU rate.
 // Off; kept for the day the pipeline is deeper.
+#ifdef ABCGPT_POLY_EXP
+constexpr bool kPolyExp = true;
+#else
 constexpr bool kPolyExp = false;
+#endif
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   x.x = fmaxf(x.x, -126.f);
   x.y = fmaxf(x.y, -126.f);

@@ -84,6 +84,7 @@ struct Cfg {
 // the GELU / GELU' epilogues were the bottleneck of their GEMMs (accumulator-empty waits of 25-40 % on the MMA issuer,
 // tools/gemm_stats.py).  Here: 15-16 FMA-pipe instructions + 2 MUFU per pair.
 constexpr float kGeluClamp = 6.5f;
+__device__ __forceinline__ float2 f2u(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 __device__ __forceinline__ float2 ex2_2(float2 a) {
   float2 e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
@@ -868,15 +869,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           if (row0 >= p.M || col0 >= p.N) continue;   // warp-uniform: the whole chunk lies outside the matrix
           uint32_t pk[16];
-          pack_chunk(p, col0, r, pk);
           if constexpr (EPI == ABCGPT_EPI_DGELU) {
+            // dH = acc * gelu'(h), one rounding.  (The reference's gelu_backward sees the dgrad output already rounded to bf16;
+            // multiplying the fp32 accumulator skips that intermediate rounding — closer to the fp32 gradient, and three
+            // instructions per column pair less in an epilogue that is the bottleneck of its GEMM.)
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const uint32_t hw = aux[c].v[i >> 3].v[i & 7];
               const float2 hx = make_float2(ptx::bf16lo(hw), ptx::bf16hi(hw));
-              const float2 d = __fmul2_rn(make_float2(ptx::bf16lo(pk[i]), ptx::bf16hi(pk[i])), p.act_tanh ? gelu_tanh_bwd2(hx) : gelu_bwd2(hx));
+              const float2 d = __fmul2_rn(f2u(r[2 * i], r[2 * i + 1]), p.act_tanh ? gelu_tanh_bwd2(hx) : gelu_bwd2(hx));
               pk[i] = ptx::pack_bf16x2(d.x, d.y);
             }
+          } else {
+            pack_chunk(p, col0, r, pk);
           }
           const uint32_t buf0 = (EPI == ABCGPT_EPI_GELU) ? stg : stg + (c & 1) * 2048;
           if (lane == 0) ptx::tma_store_wait_read<1>();   // the store that last read this buffer has drained (see Cfg2S)

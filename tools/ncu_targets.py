@@ -31,6 +31,13 @@ if "gemm" in which:
     xo = torch.empty(M, C, device=dev)
     wp = torch.randn(C, C, device=dev).bfloat16()
     ops.gemm(x, wp, epilogue=ops.EPI_RESID, out=xo, aux=resid)              # c_proj + residual
+    h = torch.empty(M, 4 * C, device=dev, dtype=torch.bfloat16)
+    g = torch.empty(M, 4 * C, device=dev, dtype=torch.bfloat16)
+    ops.gemm(x, wfc, epilogue=ops.EPI_GELU, out=h, out2=g)                   # c_fc + GELU (two TMA-store streams)
+    wpr = torch.randn(C, 4 * C, device=dev).bfloat16()
+    dh = torch.empty(M, 4 * C, device=dev, dtype=torch.bfloat16)
+    ops.gemm(x, wpr, b_mn=True, epilogue=ops.EPI_DGELU, out=dh, aux=h)       # dgrad of mlp.c_proj + GELU'
+    ops.gemm(g, wpr, epilogue=ops.EPI_RESID, out=xo, aux=resid)              # mlp.c_proj + residual (K = 3072)
 if "attn" in which:
     qkv = torch.randn(B * T, 3 * C, device=dev).bfloat16()
     o = torch.empty(B * T, C, device=dev, dtype=torch.bfloat16)
@@ -53,6 +60,7 @@ if "ln" in which:
     dw = torch.zeros(C, device=dev)
     for _ in range(REP):
         ops.layernorm_fwd(x, w, None, y, st[0], st[1])
+        ops.layernorm_fwd_resid(x, dy, dxo, w, None, y, st[0], st[1])   # residual add fused in front of the normalisation
         ops.layernorm_bwd(dy, x, w, st[0], st[1], dres, dxo, dxb, dw, None)
 if "adamw" in which:
     n = 85813248
