@@ -1076,6 +1076,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   ABCGPT_CHECK_ARG(drop_p == 0.f || (epi == ABCGPT_EPI_RESID && drop_p > 0.f && drop_p < 1.f),
                    "gemm: dropout is fused into the RESID epilogue only (0 <= p < 1)");
   ABCGPT_CHECK_ARG(epi != ABCGPT_EPI_GELU || c2 != nullptr, "gemm: GELU epilogue needs the second output");
+  ABCGPT_CHECK_ARG(epi != ABCGPT_EPI_DGELU || bias == nullptr, "gemm: the GELU' epilogue (a dgrad) takes no bias");
   ABCGPT_CHECK_ARG((epi != ABCGPT_EPI_RESID && epi != ABCGPT_EPI_DGELU) || aux != nullptr,
                    "gemm: epilogue %d needs the aux input", epi);
 
