@@ -624,12 +624,64 @@ class GPT(nn.Module):
         loss, _ = _GPTEmbedsStep.apply(anchor, self, first_embeds, idx, targets, False, 2)
         return loss
 
+    def next_logits_with_first(self, idx, first_embeds):
+        """Inference branch of `forward_with_first`: fp32 logits [B, V] of the token that follows `idx` [B, t] when the first
+        position's embedding is `first_embeds` [B, C] (tunesformer/utils.py:156-177, CharLevelDecoder.generate)."""
+        with torch.no_grad():
+            bufs = self._forward_plan(idx, None, keep_activations=False, first=first_embeds)
+        return bufs.last_logits[:, :self.config.vocab_size].float()
+
     def _anchor_tensor(self, device):
         t = getattr(self, "_anchor", None)
         if t is None or t.device != device:
             t = torch.zeros(1, device=device, requires_grad=True)
             object.__setattr__(self, "_anchor", t)
         return t
+
+    _HF_SHAPES = {"gpt2": (12, 12, 768), "gpt2-medium": (24, 16, 1024), "gpt2-large": (36, 20, 1280), "gpt2-xl": (48, 25, 1600)}
+    _HF_CONV1D = ("attn.c_attn.weight", "attn.c_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight")
+
+    def load_hf_gpt2_state_dict(self, sd_hf):
+        """Copies a HuggingFace `GPT2LMHeadModel` state dict into this module (nanoGPT/model.py:236-259): the mask buffers
+        (`.attn.bias`, `.attn.masked_bias`) are dropped, the four Conv1D weights per block are stored [in, out] there and are
+        transposed here, everything else is copied under the same name.  Shapes must agree exactly."""
+        own = self.state_dict()
+        src = {k: v for k, v in sd_hf.items() if not (k.endswith(".attn.masked_bias") or k.endswith(".attn.bias"))}
+        if len(src) != len(own):
+            raise ValueError(f"mismatched keys: {len(src)} != {len(own)}")
+        out = {}
+        for k, v in src.items():
+            if k not in own:
+                raise KeyError(f"unexpected key in the GPT-2 checkpoint: {k}")
+            v = v.detach()
+            if k.endswith(self._HF_CONV1D):
+                v = v.t()
+            if tuple(v.shape) != tuple(own[k].shape):
+                raise ValueError(f"shape mismatch for {k}: {tuple(v.shape)} vs {tuple(own[k].shape)}")
+            out[k] = v.contiguous()
+        self.load_state_dict(out)
+        return self
+
+    @classmethod
+    def from_pretrained(cls, model_type, override_args=None):
+        """`GPT.from_pretrained('gpt2' | 'gpt2-medium' | 'gpt2-large' | 'gpt2-xl', dict(dropout=...))` as in the reference
+        (nanoGPT/model.py:206-261; `train.py:197-205` init_from='gpt2*', `sample.py:67-69`): vocab 50257, block 1024,
+        bias=True, weights from `transformers.GPT2LMHeadModel.from_pretrained` (needs the HF cache or network access)."""
+        if model_type not in cls._HF_SHAPES:
+            raise ValueError(f"unknown GPT-2 checkpoint {model_type!r}")
+        override_args = override_args or {}
+        if any(k != "dropout" for k in override_args):
+            raise ValueError("only dropout can be overridden")
+        from transformers import GPT2LMHeadModel
+        print("loading weights from pretrained gpt: %s" % model_type)
+        n_layer, n_head, n_embd = cls._HF_SHAPES[model_type]
+        print("forcing vocab_size=50257, block_size=1024, bias=True")
+        args = dict(n_layer=n_layer, n_head=n_head, n_embd=n_embd, vocab_size=50257, block_size=1024, bias=True)
+        if "dropout" in override_args:
+            print(f"overriding dropout rate to {override_args['dropout']}")
+            args["dropout"] = override_args["dropout"]
+        model = cls(GPTConfig(**args))
+        return model.load_hf_gpt2_state_dict(GPT2LMHeadModel.from_pretrained(model_type).state_dict())
 
     def crop_block_size(self, block_size):
         assert block_size <= self.config.block_size

@@ -11,14 +11,114 @@ the same kernel as on the nanoGPT path; the joins are `GPT.forward_hidden` / `GP
 """
 from __future__ import annotations
 
+import random
+import re
+
+import numpy as np
 import torch
 import torch.nn as nn
 
 from . import ops
 from .model import GPT, GPTConfig
 
-PATCH_SIZE = 32      # tunesformer/config.py:1
+PATCH_SIZE = 32      # tunesformer/config.py:2
+PATCH_LENGTH = 128   # tunesformer/config.py:1
 CHAR_VOCAB = 128     # one-hot width per character (utils.py:102)
+
+
+class Patchilizer:
+    """Bar <-> patch codec of the hierarchical model (behaviour of tunesformer/utils.py:9-82; host-side, pure Python).
+
+    A tune is cut at bar lines; every bar (with its closing delimiter) and every header line becomes one patch of PATCH_SIZE
+    character codes: bos (1), the characters, eos (2), padded with 0.  (The reference passes the text through `unidecode`
+    first; that package is optional here and plain ASCII input is unchanged by it.)"""
+
+    DELIMS = ("|:", "::", ":|", "[|", "||", "|]", "|")
+    pad_token_id, bos_token_id, eos_token_id = 0, 1, 2
+
+    def __init__(self):
+        self._split = re.compile("(" + "|".join(re.escape(d) for d in self.DELIMS) + ")")
+
+    def split_bars(self, body):
+        parts = [x for x in self._split.split("".join(body)) if x]
+        if parts and parts[0] in self.DELIMS:       # a leading bar line belongs to the first bar
+            parts[1] = parts[0] + parts[1]
+            parts = parts[1:]
+        return [parts[2 * i] + parts[2 * i + 1] for i in range(len(parts) // 2)]
+
+    def bar2patch(self, bar, patch_size=PATCH_SIZE):
+        codes = ([self.bos_token_id] + [ord(c) for c in bar] + [self.eos_token_id])[:patch_size]
+        return codes + [self.pad_token_id] * (patch_size - len(codes))
+
+    def patch2bar(self, patch):
+        return "".join(chr(t) for t in patch if t > self.eos_token_id)
+
+    def encode(self, abc_code, patch_length=PATCH_LENGTH, patch_size=PATCH_SIZE, add_special_patches=False):
+        try:
+            from unidecode import unidecode
+            abc_code = unidecode(abc_code)
+        except ImportError:
+            pass
+        patches, body = [], ""
+
+        def flush(last_newline):
+            bars = self.split_bars(body)
+            for i, bar in enumerate(bars):
+                patches.append(self.bar2patch(bar + "\n" if (last_newline and i == len(bars) - 1) else bar, patch_size))
+
+        for line in (ln for ln in abc_code.split("\n") if ln):
+            header = len(line) > 1 and ((line[0].isalpha() and line[1] == ":") or line.startswith("%%score"))
+            if header:
+                if body:
+                    flush(True)
+                    body = ""
+                patches.append(self.bar2patch(line + "\n", patch_size))
+            else:
+                body += line + "\n"
+        if body:
+            flush(False)
+        if add_special_patches:
+            patches = ([[self.bos_token_id] * (patch_size - 1) + [self.eos_token_id]] + patches +
+                       [[self.bos_token_id] + [self.eos_token_id] * (patch_size - 1)])
+        return patches[:patch_length]
+
+    def decode(self, patches):
+        return "".join(self.patch2bar(p) for p in patches)
+
+
+# ---- sampling helpers -------------------------------------------------------------------------------------------------
+# The reference draws the next character with the third-party `samplings` package (top_p_sampling, top_k_sampling with
+# return_probs=True, then temperature_sampling; tunesformer/utils.py:6,247-250).  The package is not vendored in the reference
+# and is absent here, so these are restatements of its documented behaviour, not pinned to it: nucleus filter = keep the most
+# probable characters up to and including the one that takes the cumulative probability to top_p, top-k filter = keep the k
+# most probable (0 = all), both renormalise; the draw raises the probabilities to 1 / temperature, renormalises and samples
+# with numpy's seeded generator.  With top_k = 1 every variant is the argmax, which is what the golden test pins.
+def top_p_filter(probs, top_p):
+    if top_p >= 1.0:
+        return probs
+    order = np.argsort(-probs, kind="stable")
+    csum = np.cumsum(probs[order])
+    keep = order[: int(np.searchsorted(csum, top_p, side="left")) + 1]
+    out = np.zeros_like(probs)
+    out[keep] = probs[keep]
+    return out / out.sum()
+
+
+def top_k_filter(probs, top_k):
+    if top_k <= 0 or top_k >= probs.size:
+        return probs
+    keep = np.argsort(-probs, kind="stable")[:top_k]
+    out = np.zeros_like(probs)
+    out[keep] = probs[keep]
+    return out / out.sum()
+
+
+def temperature_draw(probs, temperature, seed=None):
+    if temperature <= 0.0 or np.count_nonzero(probs) == 1:
+        return int(np.argmax(probs))
+    p = np.power(probs.astype(np.float64), 1.0 / temperature)
+    p /= p.sum()
+    return int(np.random.RandomState(seed).choice(p.size, p=p))
 
 
 class _PatchEmbed(torch.autograd.Function):
@@ -92,6 +192,79 @@ class TunesFormerShaped(nn.Module):
         y[:, :-1] = chars[:, 1:]
         y[y == self.pad_token_id] = -1                                       # labels -100 at pads (utils.py:128-129)
         return self.char_level_decoder.forward_with_first(chars, first, y)
+
+    @torch.no_grad()
+    def generate(self, patches, tokens=None, top_p=1.0, top_k=0, temperature=1.0, seed=None):
+        """One more patch for every tune of the batch (tunesformer/utils.py:221-255, there for a single tune).
+
+        patches int64 [N, P, PATCH_SIZE] (or [P, PATCH_SIZE]): the tunes so far; `tokens` (optional, int64 [t] starting with
+        bos): characters of the new patch that are already fixed (a prompt that ends inside a bar).  The patch-level decoder
+        encodes the patches, the character-level decoder then spells the next patch one character at a time from the last
+        patch's encoding — every step is one forward of all still-running tunes through the sm_100a kernels; a tune stops at
+        eos or after PATCH_SIZE - 1 characters.  Returns (generated patches: one list of character codes per tune — a bare
+        list when a single tune was given, like the reference —, the seed to pass to the next call)."""
+        single = patches.dim() == 2 or patches.shape[0] == 1
+        if patches.dim() == 2:
+            patches = patches.unsqueeze(0)
+        patches = patches.reshape(patches.shape[0], -1, PATCH_SIZE)
+        N = patches.shape[0]
+        dev = patches.device
+        eos = 2
+        first = self.patch_level_decoder.encode(patches)[:, -1, :].contiguous()           # [N, C]
+        if tokens is None:
+            tokens = torch.tensor([1], device=dev)
+        seq = tokens.reshape(1, -1).to(dev).repeat(N, 1)                                    # [N, t]
+        out = [[] for _ in range(N)]
+        alive = list(range(N))
+        rng = random.Random(seed)
+        n_seed = None
+        while alive:
+            if seed is not None:                      # the reference re-seeds Python's generator with every draw
+                n_seed = rng.randint(0, 1000000)
+                rng.seed(n_seed)
+            rows = torch.tensor(alive, device=dev)
+            logits = self.char_level_decoder.next_logits_with_first(seq[rows].contiguous(), first[rows].contiguous())
+            probs = torch.softmax(logits, dim=-1).cpu().numpy()
+            nxt = []
+            for j, i in enumerate(alive):
+                p = top_k_filter(top_p_filter(probs[j], top_p), top_k)
+                tok = temperature_draw(p, temperature, None if n_seed is None else n_seed + j)
+                out[i].append(tok)
+                nxt.append(tok)
+            done = seq.shape[1] >= PATCH_SIZE - 1
+            keep = [k for k, tok in enumerate(nxt) if tok != eos and not done]
+            if not keep:
+                break
+            col = torch.zeros(N, 1, dtype=seq.dtype, device=dev)
+            col[rows, 0] = torch.tensor(nxt, device=dev, dtype=seq.dtype)
+            seq = torch.cat([seq, col], dim=1)
+            alive = [alive[k] for k in keep]
+        return (out[0] if single else out), n_seed
+
+    @torch.no_grad()
+    def generate_tune(self, prompt, max_patch=PATCH_LENGTH, top_p=0.8, top_k=8, temperature=1.2, seed=None):
+        """The tune loop of tunesformer/generate.py:128-155 for one prompt (ABC header / opening bars as text): bar patches are
+        generated and appended until the model emits an end patch, an empty bar, or `max_patch` patches.  Returns the text."""
+        pz = Patchilizer()
+        dev = next(self.parameters()).device
+        patches = torch.tensor([pz.encode(prompt, add_special_patches=True)[:-1]], device=dev)
+        prefix = pz.decode(patches[0].tolist())
+        remaining = prompt[len(prefix):]
+        tokens = torch.tensor([pz.bos_token_id] + [ord(c) for c in remaining], device=dev) if prompt else None
+        tune = prompt
+        while patches.shape[1] < max_patch:
+            patch, seed = self.generate(patches, tokens, top_p=top_p, top_k=top_k, temperature=temperature, seed=seed)
+            tokens = None
+            if patch[0] == pz.eos_token_id:
+                break
+            bar = pz.decode([patch])
+            if bar == "":
+                break
+            tune += bar
+            nxt = torch.tensor([[pz.bar2patch(remaining + bar)]], device=dev)
+            remaining = ""
+            patches = torch.cat([patches, nxt], dim=1)
+        return tune
 
     def configure_optimizers(self, weight_decay, learning_rate, betas, device_type="cuda"):
         return _Optimizers([self.patch_level_decoder.configure_optimizers(weight_decay, learning_rate, betas, device_type),

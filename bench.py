@@ -381,9 +381,13 @@ def main():
                      "achieved": achieved_tf, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved_tf / pk["sustained"],
                      "peak_kind": f"{pk['source']} sustained cuBLAS bf16", "launches_per_step": gemm_calls,
                      "avg_launch_ms": gemm_ms / gemm_calls, "flops_per_step": gemm_fl,
-                     # DRAM bytes per launch (read + write) from profiles/r1c_ncu_full_summary.md: mean of the captured
-                     # forward / dgrad / wgrad / residual instantiations at the cfg3 shapes
-                     "traffic": 220e6 if args.workload == "cfg3" else None},
+                     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) are NOT measured by this run: the
+                     # figure is the launch-weighted mean over the twelve GEMM launches of a block at the cfg3 shapes, seven
+                     # roles captured by ncu (profiles/r2_ncu_gemm.md), the other five from their operand sizes (the captured
+                     # roles' traffic equals their algorithmic bytes); null for other workloads
+                     "traffic": 240e6 if args.workload == "cfg3" else None,
+                     "traffic_source": "profiles/r2_ncu_gemm.md (ncu capture per role, launch-weighted mean; not re-measured per run)"
+                     if args.workload == "cfg3" else None},
         "kernel_breakdown": fam,
     }
     if not args.no_cpu_baseline:

@@ -23,6 +23,9 @@ SPEC = dict(
 )
 
 
+GEN_WTE_SCALE = 40.0
+
+
 def inputs(spec):
     pc, cc = O.OracleConfig(**spec["patch_cfg"]), O.OracleConfig(**spec["char_cfg"])
     psd, csd = O.synthetic_state(pc, seed=spec["patch_seed"]), O.synthetic_state(cc, seed=spec["char_seed"])
@@ -90,6 +93,53 @@ def main():
     with open(path, "w") as f:
         json.dump({"spec": SPEC, "reference": rec, "transformers": __import__("transformers").__version__}, f, indent=1)
     print("wrote", path, "loss", rec["loss"])
+
+    # ---- generation (tunesformer/utils.py:221-255) under a GREEDY sampler: `samplings` is absent, so the three helpers the
+    # reference imports from it are stubbed as pass-through filters + argmax; the fixture pins everything else of the loop
+    # (patch encoding, first-embedding substitution, stop rules) and the character-level logits through their arg-max / margins.
+    import numpy as np
+    ref.top_p_sampling = lambda prob, top_p=1, return_probs=True: prob
+    ref.top_k_sampling = lambda prob, top_k=0, return_probs=True: prob
+    margins = []
+
+    def greedy(prob, temperature=1, seed=None):
+        o = np.sort(prob)[::-1]
+        margins.append(float(o[0] - o[1]))
+        return int(np.argmax(prob))
+
+    ref.temperature_sampling = greedy
+    model.eval()
+    # closed-form weights give nearly flat next-character distributions (top-2 margins ~1e-5): for a decision that survives bf16
+    # arithmetic the tied character embedding / head matrix is scaled up (GEN_WTE_SCALE), which sharpens the logits
+    with torch.no_grad():
+        model.char_level_decoder.base.transformer.wte.weight.mul_(GEN_WTE_SCALE)
+        model.char_level_decoder.base.lm_head.weight.copy_(model.char_level_decoder.base.transformer.wte.weight)
+    pz = ref.Patchilizer()
+    seq = patches[:, :5, :].clone()
+    gen = []
+    with torch.no_grad():
+        for _ in range(4):
+            patch, _ = model.generate(seq.reshape(1, -1), None, top_p=1, top_k=0, temperature=1, seed=None)
+            gen.append([int(t) for t in patch])
+            if patch[0] == pz.eos_token_id:
+                break
+            bar = pz.decode([patch])
+            if bar == "":
+                break
+            seq = torch.cat([seq, torch.tensor([[pz.bar2patch(bar)]])], dim=1)
+        fixed = torch.tensor([1, 70, 71])     # a prompt that ends inside a bar: bos + two fixed characters
+        patch2, _ = model.generate(patches[:, :5, :].reshape(1, -1), fixed, top_p=1, top_k=0, temperature=1, seed=None)
+    texts = ["X:1\nL:1/8\nM:3/4\nK:D\n de |\"D\" fa fd AF | \"G\" GB dB GB |]\n",
+             "S:2\nB:9\nE:4\nB:9\nL:1/8\nM:3/4\nK:D\n de |\"D\" ",
+             "|: A2 B2 :: c4 d4 e4 f4 g4 a4 b4 c'4 d'4 e'4 f'4 :|\n%%score 1 2\nV:1\n[| z8 || x | y |]",
+             "K:G\nabc"]
+    codec = [{"text": t, "plain": pz.encode(t), "special": pz.encode(t, add_special_patches=True),
+              "decoded": pz.decode(pz.encode(t, add_special_patches=True))} for t in texts]
+    path = os.path.join(ROOT, "tests", "golden", "tunesformer_tiny_generate.json")
+    with open(path, "w") as f:
+        json.dump({"spec": SPEC, "n_prompt_patches": 5, "generated": gen, "margins": margins, "with_fixed_tokens": [int(t) for t in patch2],
+                   "fixed_tokens": fixed.tolist(), "char_wte_scale": GEN_WTE_SCALE, "codec": codec, "sampler": "greedy stub (samplings absent)"}, f, indent=1)
+    print("wrote", path, "patches", [len(g) for g in gen], "min margin", min(margins))
 
 
 if __name__ == "__main__":

@@ -78,11 +78,15 @@ def main():
     s = load_settings(DEFAULTS, sys.argv[1:])
     torch.manual_seed(s["seed"])
     torch.cuda.manual_seed(s["seed"])
-    if s["init_from"] != "resume":
-        raise SystemExit("init_from='gpt2*' needs the HF hub (no network); sample from a checkpoint directory")
-    ckpt = torch.load(os.path.join(s["out_dir"], "ckpt.pt"), map_location="cpu")
-    model = GPT(GPTConfig(**ckpt["model_args"]))
-    model.load_state_dict({k.removeprefix("_orig_mod."): v for k, v in ckpt["model"].items()})
+    if s["init_from"] == "resume":
+        ckpt = torch.load(os.path.join(s["out_dir"], "ckpt.pt"), map_location="cpu")
+        model = GPT(GPTConfig(**ckpt["model_args"]))
+        model.load_state_dict({k.removeprefix("_orig_mod."): v for k, v in ckpt["model"].items()})
+    elif s["init_from"].startswith("gpt2"):
+        ckpt = {}   # nanoGPT/sample.py:67-69: a given GPT-2 model (transformers: needs the HF cache or network access)
+        model = GPT.from_pretrained(s["init_from"], dict(dropout=0.0))
+    else:
+        raise SystemExit(f"unknown init_from {s['init_from']!r} (resume | gpt2*)")
     model.eval().to(s["device"])
 
     meta_path = os.path.join("data", ckpt.get("config", {}).get("dataset", s["dataset"]), "meta.pkl")

@@ -222,3 +222,53 @@ def test_dynamic_tile_scheduler_ticket_protocol_model():
                 done_items.append(nxt)
         assert sorted(done_items) == list(range(total_work)), (trial, num_pairs, total_work)
         assert end_tickets == [1] * num_pairs and resets[0] == 1 and counter[0] == 0
+
+
+def test_from_pretrained_weight_mapping_matches_the_reference_rules():
+    """GPT.load_hf_gpt2_state_dict (the body of from_pretrained, nanoGPT/model.py:236-259) on a randomly initialised HF GPT-2
+    of a small shape: Conv1D weights transposed, mask buffers dropped, tied head, everything else copied verbatim.  (The
+    hub download itself needs network access and is not exercised.)"""
+    transformers = pytest.importorskip("transformers")
+    from ai_music_generation_b200 import GPT, GPTConfig
+    torch.manual_seed(0)
+    hf = transformers.GPT2LMHeadModel(transformers.GPT2Config(n_layer=2, n_head=2, n_embd=128, vocab_size=300, n_positions=64))
+    sd_hf = hf.state_dict()
+    m = GPT(GPTConfig(block_size=64, vocab_size=300, n_layer=2, n_head=2, n_embd=128, dropout=0.0, bias=True))
+    m.load_hf_gpt2_state_dict(sd_hf)
+    sd = m.state_dict()
+    assert torch.equal(sd["transformer.h.1.mlp.c_fc.weight"], sd_hf["transformer.h.1.mlp.c_fc.weight"].t())
+    assert torch.equal(sd["transformer.h.0.attn.c_attn.weight"], sd_hf["transformer.h.0.attn.c_attn.weight"].t())
+    assert torch.equal(sd["transformer.h.0.attn.c_attn.bias"], sd_hf["transformer.h.0.attn.c_attn.bias"])
+    assert torch.equal(sd["transformer.wpe.weight"], sd_hf["transformer.wpe.weight"])
+    assert torch.equal(sd["lm_head.weight"], sd_hf["transformer.wte.weight"]) and torch.equal(sd["transformer.ln_f.weight"], sd_hf["transformer.ln_f.weight"])
+    with pytest.raises(ValueError):
+        GPT.from_pretrained("gpt3")
+    with pytest.raises(ValueError):
+        GPT.from_pretrained("gpt2", dict(bias=False))
+    bad = dict(sd_hf)
+    bad.pop("transformer.ln_f.bias")
+    with pytest.raises(ValueError):
+        m.load_hf_gpt2_state_dict(bad)
+
+
+def test_patchilizer_matches_the_reference_codec_and_sampling_helpers():
+    """Bar <-> patch codec against vectors produced by the UNMODIFIED reference Patchilizer (tunesformer/utils.py:9-82,
+    oracle/make_golden_tunesformer.py), and the restated sampling helpers' invariants."""
+    import json
+    import os
+    import numpy as np
+    from ai_music_generation_b200.tunesformer import Patchilizer, temperature_draw, top_k_filter, top_p_filter
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tunesformer_tiny_generate.json")) as f:
+        g = json.load(f)
+    pz = Patchilizer()
+    for c in g["codec"]:
+        assert pz.encode(c["text"]) == c["plain"], c["text"]
+        assert pz.encode(c["text"], add_special_patches=True) == c["special"], c["text"]
+        assert pz.decode(c["special"]) == c["decoded"]
+    assert pz.bar2patch("x" * 100) == [1] + [ord("x")] * 31 and pz.patch2bar([1, 65, 66, 2, 0, 0]) == "AB"
+    p = np.array([0.05, 0.4, 0.3, 0.15, 0.1])
+    assert np.allclose(top_p_filter(p, 0.6), [0, 4 / 7, 3 / 7, 0, 0]) and np.allclose(top_p_filter(p, 1.0), p)
+    assert np.allclose(top_k_filter(p, 2), [0, 4 / 7, 3 / 7, 0, 0]) and np.allclose(top_k_filter(p, 0), p)
+    assert temperature_draw(top_k_filter(p, 1), 1.2, seed=3) == 1 and temperature_draw(p, 0.0) == 1
+    draws = [temperature_draw(p, 1.0, seed=s) for s in range(400)]
+    assert abs(np.mean(np.array(draws) == 1) - 0.4) < 0.08 and temperature_draw(p, 1.0, seed=7) == temperature_draw(p, 1.0, seed=7)

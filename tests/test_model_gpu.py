@@ -420,3 +420,47 @@ def test_tunesformer_shaped_model_matches_reference_golden(cuda_device):
         for n, v in ref.items():
             got = 0.0 if named[n].grad is None else named[n].grad.norm().item()
             assert abs(got - v) <= 0.05 * v + 2e-3 * biggest, (n, got, v)
+
+
+def test_tunesformer_generation_matches_reference_under_a_greedy_sampler(cuda_device):
+    """TunesFormerShaped.generate against the UNMODIFIED reference TunesFormer.generate (tunesformer/utils.py:221-255) run with
+    a greedy stand-in for the absent `samplings` package (tests/golden/tunesformer_tiny_generate.json): four bar patches
+    generated one after the other from five prompt patches, and one patch continued from fixed leading characters.  Character
+    codes must be identical wherever the reference's own top-2 probability margin exceeds 0.03 (a patch is compared up to its
+    first low-margin position: after a legitimate flip the contexts differ)."""
+    from ai_music_generation_b200 import GPTConfig, TunesFormerShaped
+    from ai_music_generation_b200.tunesformer import Patchilizer
+    from oracle.make_golden_tunesformer import inputs
+    with open(os.path.join(GOLDEN, "tunesformer_tiny_generate.json")) as f:
+        g = json.load(f)
+    pc, cc, psd, csd, patches = inputs(g["spec"])
+    csd = dict(csd)
+    csd["transformer.wte.weight"] = csd["transformer.wte.weight"] * g["char_wte_scale"]
+    model = TunesFormerShaped(GPTConfig(**g["spec"]["patch_cfg"]), GPTConfig(**g["spec"]["char_cfg"]))
+    model.patch_level_decoder.load_state_dict({**psd, "lm_head.weight": psd["transformer.wte.weight"]})
+    model.char_level_decoder.load_state_dict({**csd, "lm_head.weight": csd["transformer.wte.weight"]})
+    model = model.to(cuda_device).eval()
+    pz = Patchilizer()
+    seq = patches[:, :g["n_prompt_patches"], :].to(cuda_device)
+    margins = iter(g["margins"])
+    compared = 0
+    for want in g["generated"]:
+        got, _ = model.generate(seq, None, top_p=1.0, top_k=1, temperature=1.0)
+        ms = [next(margins) for _ in want]
+        assert len(got) == len(want)
+        for a, b, m in zip(got, want, ms):
+            if m < 0.03:
+                break
+            assert a == b, (got, want)
+            compared += 1
+        seq = torch.cat([seq, torch.tensor([[pz.bar2patch(pz.decode([want]))]], device=cuda_device)], dim=1)
+    fixed = torch.tensor(g["fixed_tokens"], device=cuda_device)
+    got2, _ = model.generate(patches[:, :g["n_prompt_patches"], :].to(cuda_device), fixed, top_p=1.0, top_k=1, temperature=1.0)
+    ms = [next(margins) for _ in g["with_fixed_tokens"]]
+    n_ok = next((i for i, m in enumerate(ms) if m < 0.03), len(ms))
+    assert got2[:n_ok] == g["with_fixed_tokens"][:n_ok] and len(got2) == len(g["with_fixed_tokens"])
+    assert compared >= 60
+    # a batch of tunes advances together and gives every tune the tokens it gets alone
+    both, _ = model.generate(torch.cat([patches[:, :5, :], patches[:, 3:8, :]]).to(cuda_device), None, top_k=1)
+    alone, _ = model.generate(patches[:, 3:8, :].to(cuda_device), None, top_k=1)
+    assert both[0][:8] == g["generated"][0][:8] and both[1] == alone

@@ -132,8 +132,14 @@ def main():
         sd = {k.removeprefix("_orig_mod."): v for k, v in checkpoint["model"].items()}
         model.load_state_dict(sd)
         iter_num, best_val = checkpoint["iter_num"], checkpoint["best_val_loss"]
+    elif s["init_from"].startswith("gpt2"):
+        # nanoGPT/train.py:197-205: OpenAI GPT-2 weights through transformers (needs the HF cache or network access)
+        print(f"Initializing from OpenAI GPT-2 weights: {s['init_from']}")
+        model = GPT.from_pretrained(s["init_from"], dict(dropout=s["dropout"]))
+        for k in ("n_layer", "n_head", "n_embd", "block_size", "bias", "vocab_size"):
+            model_args[k] = getattr(model.config, k)
     else:
-        raise SystemExit("init_from='gpt2*' needs the HF hub (no network); use 'scratch' or 'resume'")
+        raise SystemExit(f"unknown init_from {s['init_from']!r} (scratch | resume | gpt2*)")
     if s["block_size"] < model.config.block_size:
         model.crop_block_size(s["block_size"])
         model_args["block_size"] = s["block_size"]
