@@ -63,6 +63,7 @@ _DEBUG_SIGNATURES = {
     "abcgpt_debug_tmem_ld_bench": (c_int, [_P, c_int, c_int, c_int, _P]),
     "abcgpt_debug_pair_probe": (c_int, [_P, _P, _P, c_int, _P]),
     "abcgpt_debug_mufu_bench": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "abcgpt_debug_mufu2_bench": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "abcgpt_debug_tmem_mma_bench": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 

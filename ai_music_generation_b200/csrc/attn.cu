@@ -20,7 +20,10 @@ long long* g_attn_trace = nullptr;  // debug only (abcgpt_debug_attn_trace): per
 long long* g_attn_cta_trace = nullptr;
 // csrc/attn_pair.cu: the same backward on CTA pairs (cta_group::2 MMAs) for unpacked sequences of >= 256 positions
 int attn_bwd_pair(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int T, int H,
-                  const DropCfg& dcfg, cudaStream_t stream);  // debug only (abcgpt_debug_attn_cta_trace): {start ns, end ns, SM id, steps} per CTA
+                  const DropCfg& dcfg, cudaStream_t stream);
+// csrc/attn_fwd3.cu: the forward with three CTAs per SM (single-buffered S / O in 128 tensor-memory columns)
+int attn_fwd3(const CUtensorMap& tmQ, const CUtensorMap& tmKV, void* out, float* lse, int T, int H, int C, int BH, int nitems,
+              const DropCfg& dcfg, int seq_shift, uint32_t fBH_d, uint32_t fBH_m, uint32_t fH_d, uint32_t fH_m, cudaStream_t stream);  // debug only (abcgpt_debug_attn_cta_trace): {start ns, end ns, SM id, steps} per CTA
 
 namespace {
 
@@ -1106,6 +1109,15 @@ int attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float 
 #define ABCGPT_FWD(D, N)                                                                                                          \
   launch_k(attn_fwd_kernel<D, N>, dim3(grid), dim3(64 + 128 * N), FwdSmem::TOTAL, stream, tmQ, tmKV, o, lse, T, H, C, BH, nitems, \
            g_attn_trace, dcfg, CT, seq_shift, fBH, fH)
+  // Three CTAs per SM with single-buffered S / O (csrc/attn_fwd3.cu) for sequences of >= 256 positions: 0.110 vs 0.120 ms per
+  // layer at cfg3, 0.0196 vs 0.0205 ms at cfg2; packed short sequences (T = 32: 0.279 vs 0.273 ms at the cfg4 character level)
+  // and the tracing tools keep the two-CTA kernel.  ABCGPT_ATTN_FWD3=0 selects the two-CTA kernel everywhere (A/B runs).
+  static const bool three_ctas = [] {
+    const char* e = getenv("ABCGPT_ATTN_FWD3");
+    return e == nullptr || e[0] != '0';
+  }();
+  if (three_ctas && seq_shift == kNoPack && T >= 256 && g_attn_trace == nullptr && CT == nullptr)
+    return attn_fwd3(tmQ, tmKV, out, lse, T, H, C, BH, nitems, dcfg, seq_shift, fBH.d, fBH.m, fH.d, fH.m, stream);
   // the step traces (abcgpt_debug_attn_trace) instrument the four-warp form
   const bool two = nh == 2 && g_attn_trace == nullptr;
   if (dcfg.thr16 == 0) { if (two) ABCGPT_FWD(false, 2); else ABCGPT_FWD(false, 1); }

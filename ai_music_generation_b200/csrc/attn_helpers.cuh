@@ -49,8 +49,10 @@ __device__ __forceinline__ float ex2(float x) {
 // Off; kept for the day the pipeline is deeper.
 #ifdef ABCGPT_POLY_EXP
 constexpr bool kPolyExp = true;
+constexpr int kPolyEvery = ABCGPT_POLY_EXP;   // every kPolyEvery-th column pair of a chunk goes to the FMA pipe (2 = half of them)
 #else
 constexpr bool kPolyExp = false;
+constexpr int kPolyEvery = 2;
 #endif
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   x.x = fmaxf(x.x, -126.f);
@@ -66,7 +68,7 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 }
 // exponentials of column pair i of a chunk: MUFU for even pairs, FMA pipe for odd ones
 __device__ __forceinline__ float2 ex2_pair(float2 t, int i) {
-  if (kPolyExp && (i & 1)) return ex2_poly2(t);
+  if (kPolyExp && (i % kPolyEvery) == kPolyEvery - 1) return ex2_poly2(t);
   return make_float2(ex2(t.x), ex2(t.y));
 }
 
@@ -314,8 +316,8 @@ __device__ __forceinline__ void fwd_chunk(uint32_t taddr, int lane, float neg_m,
     m1 = fmaxf(m1, fmaxf(s2, s3));
     const float2 t0 = __ffma2_rn(make_float2(s0, s1), sl, nm);
     const float2 t1 = __ffma2_rn(make_float2(s2, s3), sl, nm);
-    float2 p0 = ex2_pair(t0, 0);  // masked entries: 2^(-huge) = 0
-    float2 p1 = ex2_pair(t1, 1);
+    float2 p0 = ex2_pair(t0, i);  // masked entries: 2^(-huge) = 0
+    float2 p1 = ex2_pair(t1, i + 1);
     acc0 = __fadd2_rn(acc0, p0);
     acc1 = __fadd2_rn(acc1, p1);
     pk[i] = ptx::pack_bf16x2(p0.x, p0.y);

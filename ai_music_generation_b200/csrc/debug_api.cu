@@ -14,6 +14,7 @@ int mma2_bench(long long*, int, int, cudaStream_t);
 int pair_probe(const void*, const void*, float*, int, cudaStream_t);
 int mufu_bench(long long*, float*, int, int, int, cudaStream_t);
 int tmem_mma_bench(long long*, int, int, int, int, int, int, cudaStream_t);
+int mufu2_bench(long long*, float*, int, int, int, cudaStream_t);
 }  // namespace abcgpt
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
@@ -57,6 +58,11 @@ int abcgpt_debug_mufu_bench(void* out, void* sink, int iters, int warps, int mod
  * out[0] = MMA chain cycles, out[2 + w] = cycles of `iters` x (inflight x ld (x16: 32x32b.x16, else .x32) + wait) on load warp w */
 int abcgpt_debug_tmem_mma_bench(void* out, int iters, int nwarps, int x16, int inflight, int mma_n, int mma_iters, void* stream) {
   return abcgpt::tmem_mma_bench(reinterpret_cast<long long*>(out), iters, nwarps, x16, inflight, mma_n, mma_iters, S(stream));
+}
+
+/* debug: MUFU.EX2 rate by operand format, compile-time modes (csrc/microbench.cu mufu2_bench_kernel); out[warp] = cycles */
+int abcgpt_debug_mufu2_bench(void* out, void* sink, int iters, int warps, int mode, void* stream) {
+  return abcgpt::mufu2_bench(reinterpret_cast<long long*>(out), reinterpret_cast<float*>(sink), iters, warps, mode, S(stream));
 }
 
 int abcgpt_debug_attn_trace(void* device_stamps) {

@@ -436,3 +436,73 @@ int tmem_mma_bench(long long* out, int iters, int nwarps, int x16, int inflight,
   return launch_status("tmem_mma_bench_kernel");
 }
 }  // namespace abcgpt
+
+// ---- debug micro-benchmark: MUFU.EX2 rate by operand format, compile-time modes (tools/mufu2_bench.py) -------------------
+// The run-time `mode` dispatch of mufu_bench_kernel sits inside its inner loop and dominates its timing; here every format is
+// its own instantiation: 16 independent dependency chains per thread, `iters` rounds.  MODE 0: ex2.approx.ftz.f32 (one result
+// per lane-op); 1: ex2.approx.f16x2; 2: ex2.approx.ftz.bf16x2 (two results per lane-op if the unit is really packed);
+// 3: the softmax pattern fma.f32x2 + 2 x ex2.f32 + cvt.bf16x2; 4: fma.f32x2 + cvt.f16x2 + ex2.f16x2 (the packed alternative).
+namespace abcgpt {
+namespace {
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) mufu2_bench_kernel(long long* out, float* sink, int iters) {
+  float x[16];
+  uint32_t h[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    x[i] = -0.001f * static_cast<float>((threadIdx.x & 63) + i);
+    h[i] = 0xB800B400u + i;  // two small negative halves
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if constexpr (MODE == 0) {
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+        x[i] = -x[i];
+      } else if constexpr (MODE == 1) {
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[i]));
+        h[i] ^= 0x80008000u;
+      } else if constexpr (MODE == 2) {
+        asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(h[i]));
+        h[i] ^= 0x80008000u;
+      } else if constexpr (MODE == 3) {   // two fp32 exponentials + pack per pair (i, i^1 share a pair: 8 pairs)
+        if (i < 8) {
+          float2 t = __ffma2_rn(make_float2(x[2 * i], x[2 * i + 1]), make_float2(0.18f, 0.18f), make_float2(-1.f, -1.f));
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(t.x));
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(t.y));
+          h[i] = ptx::pack_bf16x2(t.x, t.y);
+          x[2 * i] = -t.x; x[2 * i + 1] = -t.y;
+        }
+      } else {                             // fma pair + cvt to f16x2 + ONE packed exponential per pair
+        if (i < 8) {
+          const float2 t = __ffma2_rn(make_float2(x[2 * i], x[2 * i + 1]), make_float2(0.18f, 0.18f), make_float2(-1.f, -1.f));
+          uint32_t hh;
+          asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hh) : "f"(t.y), "f"(t.x));
+          asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(hh));
+          h[i] = hh;
+          x[2 * i] = -t.x * 0.5f; x[2 * i + 1] = -t.y * 0.5f;
+        }
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc += x[i] + __uint_as_float(h[i]);
+  if (acc == 1234.5f) sink[0] = acc;
+  if ((threadIdx.x & 31) == 0) out[threadIdx.x >> 5] = t1 - t0;
+}
+}  // namespace
+int mufu2_bench(long long* out, float* sink, int iters, int warps, int mode, cudaStream_t stream) {
+  switch (mode) {
+    case 0: mufu2_bench_kernel<0><<<1, warps * 32, 0, stream>>>(out, sink, iters); break;
+    case 1: mufu2_bench_kernel<1><<<1, warps * 32, 0, stream>>>(out, sink, iters); break;
+    case 2: mufu2_bench_kernel<2><<<1, warps * 32, 0, stream>>>(out, sink, iters); break;
+    case 3: mufu2_bench_kernel<3><<<1, warps * 32, 0, stream>>>(out, sink, iters); break;
+    default: mufu2_bench_kernel<4><<<1, warps * 32, 0, stream>>>(out, sink, iters); break;
+  }
+  return launch_status("mufu2_bench_kernel");
+}
+}  // namespace abcgpt

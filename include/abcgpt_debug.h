@@ -28,6 +28,8 @@ int abcgpt_debug_tmem_ld_bench(void* out, int iters, int nwarps, int inflight, v
 int abcgpt_debug_mufu_bench(void* out, void* sink, int iters, int warps, int mode, void* stream);
 /* tcgen05.ld under tensor-core load: see csrc/microbench.cu (tools/tmem_mma_bench.py) */
 int abcgpt_debug_tmem_mma_bench(void* out, int iters, int nwarps, int x16, int inflight, int mma_n, int mma_iters, void* stream);
+/* MUFU.EX2 rate by operand format (f32, f16x2, bf16x2, the fp32 softmax pattern, the packed-f16 alternative); tools/mufu2_bench.py */
+int abcgpt_debug_mufu2_bench(void* out, void* sink, int iters, int warps, int mode, void* stream);
 int abcgpt_debug_pair_probe(const void* a, const void* b, void* d, int mode, void* stream);
 
 #ifdef __cplusplus
