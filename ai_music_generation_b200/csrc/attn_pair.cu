@@ -31,6 +31,9 @@ namespace abcgpt {
 namespace {
 
 constexpr int kSBuf = 3;          // S/dP score buffers in TMEM (as in csrc/attn.cu)
+#ifndef ABCGPT_EXP_SCORE_K
+#define ABCGPT_EXP_SCORE_K 4      // timing experiments only: fewer k-steps in the dQ kernel's score MMAs (wrong results)
+#endif
 constexpr int kRing = 6;          // streamed tiles in flight
 // Thread layout: warp 0 TMA, warp 1 score MMAs, warps 2..17 compute, warp 18 accumulating MMAs.
 // SIXTEEN compute warps (four per scheduler): the single-CTA kernels' two groups of four (two warps per scheduler, each
@@ -43,10 +46,17 @@ constexpr int kRing = 6;          // streamed tiles in flight
 // kernels are NOT latency-bound: with eight compute warps the steady state already runs at 80-90 % of the MUFU (ex2) rate, and
 // the extra warps only add per-step barrier traffic.  NCH = 1 (eight compute warps, a thread owns a whole row of a step) is the
 // default; the template parameter stays for experiments.
-template <int NCH> struct PairCfg {
-  static constexpr int kCompWarps = 8 * NCH;
+// NG = number of STEP GROUPS (dQ kernel): group g owns the steps gs with gs % NG == g.  NG = 2 alternates two groups over the
+// three score buffers (the issuer runs one step ahead); NG = 3 gives every score buffer its own group — a third independent
+// instruction stream per SM for the latency gaps of the other two (the forward gained 8 % from a third resident CTA for the
+// same reason, csrc/attn_fwd3.cu).  MEASURED: dQ kernel 0.125 -> 0.118 ms per layer at cfg3 — each group now idles ~60 % of its
+// cycle (3 x 1050 cycles per own step against ~1250 of arithmetic), i.e. the steps are not fed faster than one per ~1050 cycles
+// per SM whatever the number of groups: the score / accumulate MMA chain and its operand re-reads (Q and dO, 4 KB each per
+// MMA, are the shared-memory-bound A operands of eight of the twelve MMAs of a step) are the next thing to look at.
+template <int NCH, int NG = 2> struct PairCfg {
+  static constexpr int kCompWarps = 4 * NG * NCH;
   static constexpr int kAccWarp = 2 + kCompWarps;
-  static constexpr int kThreads = (kAccWarp + 1) * 32;   // 352 / 608
+  static constexpr int kThreads = (kAccWarp + 1) * 32;   // 352 / 608; NG = 3: 480
 };
 
 // static schedule over PAIR items: pair c of G walks items c, 2G-1-c, 2G+c, ... (heaviest first, boustrophedon)
@@ -380,8 +390,8 @@ struct Dq2Smem {
   static constexpr int TOTAL = BAR + 512 + 1024;
 };
 
-template <bool DROP, int NCH>
-__global__ void __launch_bounds__(PairCfg<NCH>::kThreads, 1)
+template <bool DROP, int NCH, int NG>
+__global__ void __launch_bounds__(PairCfg<NCH, NG>::kThreads, 1)
 attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmDO128,
                     const __grid_constant__ CUtensorMap tmKV32, const __grid_constant__ CUtensorMap tmKc,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T,
@@ -415,7 +425,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_con
       ptx::mbar_init(&qdo_full[s], 1);
       ptx::mbar_init(&qdo_empty[s], 1);
       ptx::mbar_init(&acc_full[s], 1);
-      ptx::mbar_init(&acc_free[s], 2 * PairCfg<NCH>::kCompWarps);
+      ptx::mbar_init(&acc_free[s], 2 * PairCfg<NCH, NG>::kCompWarps);
     }
     for (int s = 0; s < kRing; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
@@ -500,16 +510,16 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_con
           const uint64_t dK = dKV0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4)), dV = dK + (4096 >> 4);
           const uint32_t tS = tmem_base + (gs % kSBuf) * 128;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ss_2sm(tS, dQ0 + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
+          for (int kk = 0; kk < ABCGPT_EXP_SCORE_K; ++kk) if (leader) ptx::umma_ss_2sm(tS, dQ0 + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ss_2sm(tS + 64, dDO0 + 2 * kk, dV + 2 * kk, idesc_s, kk > 0);
+          for (int kk = 0; kk < ABCGPT_EXP_SCORE_K; ++kk) if (leader) ptx::umma_ss_2sm(tS + 64, dDO0 + 2 * kk, dV + 2 * kk, idesc_s, kk > 0);
           if (leader) ptx::umma_commit_2sm(&s_full[gs % kSBuf], 0x3);
         }
         if (leader) ptx::umma_commit_2sm(&qdo_empty[k & 1], 0x3);  // all score MMAs of the item done: Q / dO may be overwritten
       }
     }
     __syncwarp();
-  } else if (warp == PairCfg<NCH>::kAccWarp) {
+  } else if (warp == PairCfg<NCH, NG>::kAccWarp) {
     // ---- accumulating MMAs (leader CTA): dQ += dS_j K_j (accumulator double-buffered by item parity)
     if (leader_cta) {
       const bool leader = ptx::elect_one();
@@ -542,7 +552,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_con
     __syncwarp();
   } else {
     const int cw = warp - 2;                // 0 .. 8 NCH - 1
-    const int sg = cw / (4 * NCH);          // step group: owns the steps of parity sg
+    const int sg = cw / (4 * NCH);          // step group: owns the steps gs with gs % NG == sg
     const int ch = (cw >> 2) & (NCH - 1);   // NCH = 2: column half of every own step (key columns [32 ch, 32 ch + 32) of the 64)
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -569,13 +579,17 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_con
       fdivmod(bh, fH, b, h);
       const int qt = 2 * (npt - 1 - pr) + rank;
       const int t = qt * 128 + r;
-      const int colq = 2 * sg + ch;
+      // 16-column granules of the 64 dQ columns: NG = 2: group sg takes granules [2 sg + ch, + 2 / NCH); NG = 3: group 0 takes
+      // granules 0 and 1, groups 1 and 2 one each
+      const int colq = NG == 3 ? (sg == 0 ? 0 : sg + 1) : 2 * sg + ch;
+      const int nq = NG == 3 ? (sg == 0 ? 2 : 1) : 2 / NCH;
       ptx::mbar_wait(&acc_full[k & 1], (k >> 1) & 1, 77);
       ptx::tc_fence_after();
-      constexpr int NQ = 2 / NCH;   // 16-column loads per thread
+      constexpr int NQ = NG == 3 ? 2 : 2 / NCH;   // 16-column loads per thread (at most)
       uint32_t v[16 * NQ];
 #pragma unroll
-      for (int c = 0; c < NQ; ++c) ptx::tmem_ld16(tm_dQ + (k & 1) * 64 + lane_off + (colq + c) * 16, *reinterpret_cast<uint32_t(*)[16]>(v + 16 * c));
+      for (int c = 0; c < NQ; ++c)
+        if (c < nq) ptx::tmem_ld16(tm_dQ + (k & 1) * 64 + lane_off + (colq + c) * 16, *reinterpret_cast<uint32_t(*)[16]>(v + 16 * c));
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       warp_arrive_leader(&acc_free[k & 1], lane);
@@ -583,6 +597,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_con
         __nv_bfloat16* o = dqkv + static_cast<long long>(b * T + t) * (3 * C) + h * HS + colq * 16;
 #pragma unroll
         for (int q = 0; q < 2 * NQ; ++q) {
+          if (q >= 2 * nq) break;
           uint4 w;
           w.x = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
           w.y = ptx::pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
@@ -625,7 +640,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_con
         }
         stat_k = c_k;
         int nk = c_k + 1;
-        {
+        if (NG == 2) {  // (NG = 3 runs on items of at least four steps: every group owns a step of every item)
           const int nit = sched_pair_item(nk, nitems);
           if (nit >= 0 && tiles_of(nit) == 1 && ((c_base + c_nq) & 1) != sg) ++nk;
         }
@@ -651,7 +666,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_con
       ptx::tc_fence_before();
       warp_arrive_leader(&ds_full[gs % kSBuf], lane);
       while (ep_k < c_k) epilogue(ep_k++);
-      c_n += 2;
+      c_n += NG;
       normalize();
     }
     while (ep_k < c_k) epilogue(ep_k++);
@@ -706,18 +721,21 @@ int attn_bwd_pair(const void* qkv, const void* dout, const float* lse, const flo
   if ((rc = encode_tmap_2d(&tmDO32, dout, 2, static_cast<uint64_t>(C), rows, pitch_do, 64, 32, true))) return rc;
   if ((rc = encode_tmap_2d_sw(&tmDOc, dout, 2, static_cast<uint64_t>(C), rows, pitch_do, 32, 64, 64))) return rc;
   static bool done = false;
-  static int nch_dq = kNCH, nch_dkv = kNCH;
+  static int nch_dq = kNCH, nch_dkv = kNCH, ng_dq = 3;   // MEASURED (cfg3, per layer): dQ kernel with three step groups 0.118 vs 0.125 ms
   if (!done) {
-    if ((rc = set_smem(attn_bwd_dq2_kernel<false, 1>, Dq2Smem::TOTAL))) return rc;
-    if ((rc = set_smem(attn_bwd_dq2_kernel<true, 1>, Dq2Smem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dq2_kernel<false, 1, 2>, Dq2Smem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dq2_kernel<true, 1, 2>, Dq2Smem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dq2_kernel<false, 1, 3>, Dq2Smem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dq2_kernel<true, 1, 3>, Dq2Smem::TOTAL))) return rc;
     if ((rc = set_smem(attn_bwd_dkv2_kernel<false, 1>, Dkv2Smem::TOTAL))) return rc;
     if ((rc = set_smem(attn_bwd_dkv2_kernel<true, 1>, Dkv2Smem::TOTAL))) return rc;
-    if ((rc = set_smem(attn_bwd_dq2_kernel<false, 2>, Dq2Smem::TOTAL))) return rc;
-    if ((rc = set_smem(attn_bwd_dq2_kernel<true, 2>, Dq2Smem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dq2_kernel<false, 2, 2>, Dq2Smem::TOTAL))) return rc;
+    if ((rc = set_smem(attn_bwd_dq2_kernel<true, 2, 2>, Dq2Smem::TOTAL))) return rc;
     if ((rc = set_smem(attn_bwd_dkv2_kernel<false, 2>, Dkv2Smem::TOTAL))) return rc;
     if ((rc = set_smem(attn_bwd_dkv2_kernel<true, 2>, Dkv2Smem::TOTAL))) return rc;
     if (const char* e = getenv("ABCGPT_ATTN_NCH_DQ")) nch_dq = e[0] == '2' ? 2 : 1;     // experiments: compute warps 8 x NCH
     if (const char* e = getenv("ABCGPT_ATTN_NCH_DKV")) nch_dkv = e[0] == '2' ? 2 : 1;
+    if (const char* e = getenv("ABCGPT_ATTN_NG_DQ")) ng_dq = e[0] == '2' ? 2 : 3;        // step groups of the dQ kernel
     done = true;
   }
   const int BH = B * H, nitems = ((T + 255) / 256) * BH;
@@ -729,13 +747,14 @@ int attn_bwd_pair(const void* qkv, const void* dout, const float* lse, const flo
 #define ABCGPT_DKV2(D, N)                                                                                                   \
   ABCGPT_CUDA(launch_pair(attn_bwd_dkv2_kernel<D, N>, grid, PairCfg<N>::kThreads, Dkv2Smem::TOTAL, stream, tmQKV128, tmQKV32,  \
                           tmDO32, tmQKVc, tmDOc, lse, delta, dq, T, H, C, BH, nitems, dcfg, fBH, fH))
-#define ABCGPT_DQ2(D, N)                                                                                                    \
-  ABCGPT_CUDA(launch_pair(attn_bwd_dq2_kernel<D, N>, grid, PairCfg<N>::kThreads, Dq2Smem::TOTAL, stream, tmQKV128, tmDO128,    \
+#define ABCGPT_DQ2(D, N, G)                                                                                                 \
+  ABCGPT_CUDA(launch_pair(attn_bwd_dq2_kernel<D, N, G>, grid, PairCfg<N, G>::kThreads, Dq2Smem::TOTAL, stream, tmQKV128, tmDO128, \
                           tmQKV32, tmQKVc, lse, delta, dq, T, H, C, BH, nitems, dcfg, fBH, fH))
   if (nch_dkv == 2) { if (drop) ABCGPT_DKV2(true, 2); else ABCGPT_DKV2(false, 2); }
   else { if (drop) ABCGPT_DKV2(true, 1); else ABCGPT_DKV2(false, 1); }
-  if (nch_dq == 2) { if (drop) ABCGPT_DQ2(true, 2); else ABCGPT_DQ2(false, 2); }
-  else { if (drop) ABCGPT_DQ2(true, 1); else ABCGPT_DQ2(false, 1); }
+  if (nch_dq == 2) { if (drop) ABCGPT_DQ2(true, 2, 2); else ABCGPT_DQ2(false, 2, 2); }
+  else if (ng_dq == 3) { if (drop) ABCGPT_DQ2(true, 1, 3); else ABCGPT_DQ2(false, 1, 3); }
+  else { if (drop) ABCGPT_DQ2(true, 1, 2); else ABCGPT_DQ2(false, 1, 2); }
 #undef ABCGPT_DKV2
 #undef ABCGPT_DQ2
   return launch_status("attn_bwd pair kernels");
