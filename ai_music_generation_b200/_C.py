@@ -51,6 +51,8 @@ _SIGNATURES = {
     "abcgpt_colsum_bf16": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "abcgpt_replay": (c_int, [_P, c_int64, c_int64]),
     "abcgpt_set_pdl": (c_int, [c_int]),
+    "abcgpt_event_record": (c_int, [c_int, _P]),
+    "abcgpt_event_wait": (c_int, [c_int, _P]),
     "abcgpt_argmax": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P]),
     "abcgpt_sample_topk": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, c_int64, _P, c_int64, c_int, _P]),
 }

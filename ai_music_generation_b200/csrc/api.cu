@@ -182,4 +182,37 @@ int abcgpt_set_pdl(int on) {
   return 0;
 }
 
+/* Cross-stream ordering for launch plans that run independent kernels on a second stream (the weight-gradient GEMMs of the
+ * backward, ai_music_generation_b200/model.py): `abcgpt_event_record(slot, stream)` marks the work enqueued on `stream` so far,
+ * `abcgpt_event_wait(slot, stream)` makes `stream` wait (on the device) for the most recent mark of `slot`.  Slots are small
+ * integers owned by the caller; the events live per device inside the library (created on first use, no timing). */
+namespace {
+constexpr int kEventSlots = 1024, kEventDevs = 16;
+cudaEvent_t g_events[kEventDevs][kEventSlots];
+bool g_event_made[kEventDevs][kEventSlots];
+int event_of(int slot, cudaEvent_t* ev) {
+  int dev = 0;
+  ABCGPT_CUDA(cudaGetDevice(&dev));
+  if (slot < 0 || slot >= kEventSlots || dev < 0 || dev >= kEventDevs) return fail(-1, "event slot %d / device %d out of range", slot, dev);
+  if (!g_event_made[dev][slot]) {
+    ABCGPT_CUDA(cudaEventCreateWithFlags(&g_events[dev][slot], cudaEventDisableTiming));
+    g_event_made[dev][slot] = true;
+  }
+  *ev = g_events[dev][slot];
+  return 0;
+}
+}  // namespace
+int abcgpt_event_record(int slot, void* stream) {
+  cudaEvent_t ev;
+  if (int rc = event_of(slot, &ev)) return rc;
+  ABCGPT_CUDA(cudaEventRecord(ev, S(stream)));
+  return 0;
+}
+int abcgpt_event_wait(int slot, void* stream) {
+  cudaEvent_t ev;
+  if (int rc = event_of(slot, &ev)) return rc;
+  ABCGPT_CUDA(cudaStreamWaitEvent(S(stream), ev, 0));
+  return 0;
+}
+
 }  // extern "C"

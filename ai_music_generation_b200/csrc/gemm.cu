@@ -26,6 +26,11 @@ unsigned long long* g_gemm_stats = nullptr;  // debug only: set through abcgpt_d
 
 namespace {
 
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kNumEpiWarps = 16;   // four per scheduler: the epilogue arithmetic is dependency-latency bound (ncu: `wait` stalls,
@@ -636,6 +641,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t rank = crank & 1;                // CTA within its pair
   const uint32_t pr = crank >> 1;                 // pair within the cluster (QUAD: 0 / 1)
   const bool leader = rank == 0;
+  // debug timeline (p.stats, tools/gemm_timeline.py), nanoseconds of %globaltimer over all CTAs: [8] min kernel entry, [9] max
+  // "prologue done", [10] min / [11] max "first operand stage landed", [12] max "last MMA committed", [13] max "epilogue
+  // done", [14] max kernel exit, [15] min "prologue done"
+  if (p.stats && threadIdx.x == 0) atomicMin(&p.stats[8], static_cast<unsigned long long>(globaltimer_ns()));
 
   if (warp == kProdWarp && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -665,6 +674,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = ptx::uniform(*tmem_slot);
   ptx::pdl_launch_dependents();  // programmatic dependent launch: see launch_k (common.h)
   ptx::pdl_wait();               // everything above touched only this CTA's shared memory / TMEM
+  long long g_start = 0;
+  if (p.stats && threadIdx.x == 0) {
+    const unsigned long long t = static_cast<unsigned long long>(globaltimer_ns());
+    atomicMax(&p.stats[9], t);
+    atomicMin(&p.stats[15], t);
+  }
+  if (p.stats) g_start = globaltimer_ns();
 
   const int num_m_pair = (p.num_m_blk + 1) / 2;
   const int m_units = QUAD ? num_m_pair / 2 : num_m_pair;  // QUAD: the host guarantees an even number of 256-row tiles
@@ -800,6 +816,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = kb0; kb < kb1; ++kb) {
           timed_wait(&full[stage], phase, 43, p.stats, 1, w0);
           ptx::tc_fence_after();
+          if (p.stats && it == 0 && kb == kb0 && issue) {
+            const unsigned long long t = static_cast<unsigned long long>(globaltimer_ns());
+            atomicMin(&p.stats[10], t);
+            atomicMax(&p.stats[11], t);
+          }
           const uint32_t a_base = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_base = a_base + C::A_BYTES;
 #pragma unroll
@@ -821,6 +842,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (issue && p.stats) {
         atomicAdd(&p.stats[1], static_cast<unsigned long long>(w0));
         atomicAdd(&p.stats[2], static_cast<unsigned long long>(w1));
+        atomicMax(&p.stats[12], static_cast<unsigned long long>(globaltimer_ns()));
       }
     }
     __syncwarp();
@@ -868,6 +890,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[as]), crank & ~1u));
           }
           if (row0 >= p.M || col0 >= p.N) continue;   // warp-uniform: the whole chunk lies outside the matrix
+          if constexpr (EPI == ABCGPT_EPI_F32_RED) {
+            // split-K / accumulating weight gradient: the 32 x 32 fp32 chunk leaves as two [32 rows x 64 B] staging halves, each
+            // added into the gradient by ONE tensor reduction (whole 64-byte row pieces per L2 operation) instead of 32 x 8
+            // row-per-thread red.global.add.v4 (16 bytes per L2 atomic, 32 different lines per warp instruction): the exposed
+            // reduction of a pair's last tile was ~10 us of every wgrad launch (tools/gemm_timeline.py)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t buf = stg + hh * 2048;
+              if (lane == 0) ptx::tma_store_wait_read<1>();
+              __syncwarp();
+              st_stage_bf16(buf, lane, r + 16 * hh);
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0 && col0 + 16 * hh < p.N) {
+                ptx::tma_reduce_add_2d_s(&tmC, buf, col0 + 16 * hh, row0);
+                ptx::tma_store_commit();
+              }
+            }
+            continue;
+          }
           uint32_t pk[16];
           if constexpr (EPI == ABCGPT_EPI_DGELU) {
             // dH = acc * gelu'(h), one rounding.  (The reference's gelu_backward sees the dgrad output already rounded to bf16;
@@ -932,11 +974,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       atomicAdd(&p.stats[3], static_cast<unsigned long long>(w0));
       atomicAdd(&p.stats[5], static_cast<unsigned long long>(clock64() - t_start));
     }
+    if (p.stats && lane == 0) atomicMax(&p.stats[13], static_cast<unsigned long long>(globaltimer_ns()));
+    if (p.stats && warp == kEpiWarp0 && lane == 0 && blockIdx.x == 0) {  // SM clock of this launch = [6] cycles / [7] ns (CTA 0)
+      p.stats[6] = static_cast<unsigned long long>(clock64() - t_start);
+      p.stats[7] = static_cast<unsigned long long>(globaltimer_ns() - g_start);
+    }
   }
 
   ptx::tc_fence_before();
   ptx::cluster_sync_all();
   if (warp == kMmaWarp) ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+  if (p.stats && threadIdx.x == 0) atomicMax(&p.stats[14], static_cast<unsigned long long>(globaltimer_ns()));
 }
 
 // Persistent launch with a cluster dimension attribute.  `units` = work items (one per cluster); the grid is the number of
@@ -1004,6 +1052,18 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
         rc = encode_tmap_2d_sw(&tmC2, p.c2, 2, static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.ldc2) * 2, 32, 32, 64);
         if (rc) return rc;
       }
+      return launch2q<A_MN, B_MN, EPI, false, true>(tmA, tmB, tmC, tmC2, p, units, stream);
+    }
+  }
+  if constexpr (EPI == ABCGPT_EPI_F32_RED) {
+    // weight gradients: TMA tile reductions (cp.reduce.async.bulk.tensor .add) instead of per-thread red.global (see the epilogue)
+    static const bool red_on = [] {
+      const char* e = getenv("ABCGPT_GEMM_TMA_RED");
+      return e == nullptr || e[0] != '0';
+    }();
+    if (!quad && red_on && (reinterpret_cast<uintptr_t>(p.c) & 15) == 0 && ((p.ldc * 4) & 15) == 0) {
+      const int rc = encode_tmap_2d_sw(&tmC, p.c, 4, static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.ldc) * 4, 16, 32, 64);
+      if (rc) return rc;
       return launch2q<A_MN, B_MN, EPI, false, true>(tmA, tmB, tmC, tmC2, p, units, stream);
     }
   }
@@ -1086,6 +1146,14 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   const int num_k_blk = (K + BK - 1) / BK;
   int bn = bn_hint;
   if (bn == 0) {
+    static int env_tile = -1;   // experiments: ABCGPT_GEMM_TILE overrides the automatic choice (same values as the hint)
+    if (env_tile < 0) {
+      const char* e = getenv("ABCGPT_GEMM_TILE");
+      env_tile = e ? atoi(e) : 0;
+    }
+    if (env_tile > 0 && N > 128) bn = env_tile;
+  }
+  if (bn == 0) {
     // CTA pairs halve the B-operand traffic per SM (the single-CTA kernel is starved by L2->SM operand delivery);
     // they need N > 128 to be worth a 256-wide tile.
     if (N > 128) {
@@ -1100,7 +1168,7 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
   // tiles.  Measured on B200 it is a wash against plain pairs (1.32-1.37 vs 1.34-1.37 PFLOP/s on the cfg3 shapes: the L2
   // already merges the two pairs' requests, and at the ~1.2 GHz the power cap allows in GEMM loops the pair kernel runs at
   // > 90 % of the tensor peak), so it is opt-in.
-  const bool quad = pair && bn_hint == 1024 && (((M + 255) / 256) % 2 == 0);
+  const bool quad = pair && bn == 1024 && (((M + 255) / 256) % 2 == 0);
   const int tile_n = pair ? 256 : bn;
   const int num_n_blk = (N + tile_n - 1) / tile_n;
   const int num_m_units = quad ? ((num_m_blk + 1) / 2) / 2 : (pair ? (num_m_blk + 1) / 2 : num_m_blk);  // schedulable row blocks

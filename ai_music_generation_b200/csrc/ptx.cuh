@@ -102,6 +102,13 @@ __device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* tm, uint32_t s
                "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// shared -> global tile REDUCTION (fp32 add performed by the L2 on whole lines): the split-K weight-gradient epilogue
+__device__ __forceinline__ void tma_reduce_add_2d_s(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {

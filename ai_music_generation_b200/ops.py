@@ -42,6 +42,32 @@ def set_pdl(on):
     _C.lib().abcgpt_set_pdl(1 if on else 0)
 
 
+_SIDE = {}
+
+
+def side_stream():
+    """The second stream of the current device for kernels that are independent of the main chain (weight-gradient GEMMs)."""
+    dev = torch.cuda.current_device()
+    st = _SIDE.get(dev)
+    if st is None:
+        st = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def profiling():
+    return _PROFILE is not None
+
+
+def event_record(slot, stream=None):
+    """include/abcgpt.h abcgpt_event_record: mark the work enqueued so far on `stream` (default: the current one) under `slot`."""
+    _call("event_record", 0, (slot,), _C.lib().abcgpt_event_record, int(slot), _stream() if stream is None else stream.cuda_stream)
+
+
+def event_wait(slot, stream=None):
+    """abcgpt_event_wait: `stream` (default: the current one) waits on the device for the latest mark of `slot`."""
+    _call("event_wait", 0, (slot,), _C.lib().abcgpt_event_wait, int(slot), _stream() if stream is None else stream.cuda_stream)
+
+
 def record_callback(fn):
     """Interleave a Python callback (e.g. DDP bucket launch) with the recorded launches; runs now and on every replay."""
     if _RECORD is not None:

@@ -13,8 +13,10 @@
 extern "C" {
 #endif
 
-/* Debug aid: device pointer to 8 uint64 cycle counters accumulated by subsequent GEMM launches (NULL disables):
- * [0] producer empty-wait [1] MMA full-wait [2] MMA tmem-empty wait [3] epilogue tmem-full wait [5] CTA total. */
+/* Debug aid: device pointer to 16 uint64 counters accumulated by subsequent GEMM launches (NULL disables): cycles
+ * [0] producer empty-wait [1] MMA full-wait [2] MMA tmem-empty wait [3] epilogue tmem-full wait [5] CTA total; pair kernel
+ * only, %globaltimer nanoseconds over all CTAs (the caller presets the min slots to ~0): [8] min kernel entry, [9] max / [15] min
+ * prologue done, [10] min / [11] max first operand stage landed, [12] max last MMA committed, [13] max epilogue done, [14] max exit. */
 int abcgpt_debug_gemm_stats(void* device_counters);
 /* Debug aid: device pointer to int64[num_kv_tiles * 8]; one CTA of the next attention forward launches stamps clock64
  * at its phase boundaries (NULL disables). */
