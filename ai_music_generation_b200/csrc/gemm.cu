@@ -61,6 +61,8 @@ struct GemmParams {
   int wide;  // 1: every epilogue pointer / leading dimension is 32-byte aligned -> 256-bit global accesses
   DropCfg drop;  // RESID epilogue only: dropout on the Linear output before the residual add (model.py:75-76,91)
   long long head_stride;  // BF16 epilogue: != 0 -> column c of a row goes to (c / 64) * head_stride + c % 64 (head-major KV cache)
+  int half_from, half_extra;  // pair kernel: tiles >= half_from are processed as two 256 x 128 half tiles (work items
+                              // half_from + 2 j, + 2 j + 1 of tile half_from + j): see "Half tiles" above gemm2_kernel
   int* sched;  // pair kernel: global ticket counter of the dynamic tile scheduler (nullptr = static round-robin)
   unsigned long long* stats;  // optional debug counters (cycles): [0] producer empty-wait, [1] mma full-wait,
                               // [2] mma tmem-empty wait, [3] epilogue tmem-full wait, [4] epilogue busy, [5] cta total
@@ -684,7 +686,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int num_m_pair = (p.num_m_blk + 1) / 2;
   const int m_units = QUAD ? num_m_pair / 2 : num_m_pair;  // QUAD: the host guarantees an even number of 256-row tiles
-  const int total_work = m_units * p.num_n_blk * p.splits;
+  // Half tiles: with T tiles on P pairs the static schedule takes ceil(T / P) rounds; when the last round would hold r <= P / 2
+  // tiles (GPT-2-small's N = 768 layers at 32 k tokens: 384 tiles on 74 pairs = 5.19 -> 6 rounds, 13 % of the GEMM idle), those r
+  // tiles are issued as 2 r work items of 256 x 128 (MMA N = 128: the same operand boxes are loaded and the first 64 B rows /
+  // columns of each CTA used, half the MMA time, column groups 2 and 3 of the epilogue idle): the last round costs half a tile.
+  const int total_work = m_units * p.num_n_blk * p.splits + p.half_extra;
   const int pair_id = blockIdx.x / CL;      // cluster index
   const long long t_start = p.stats ? clock64() : 0;
   long long w0 = 0, w1 = 0;
@@ -749,10 +755,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int w = next_work(it);
         if (w < 0) break;
         const int split = w % p.splits;
-        const int tile = w / p.splits;
+        const bool is_half = w >= p.half_from;   // (half tiles only with splits == 1: w is the tile index below half_from)
+        const int tile = is_half ? p.half_from + ((w - p.half_from) >> 1) : w / p.splits;
         const int m_unit = tile / p.num_n_blk;
         const int m0 = (QUAD ? 2 * m_unit + static_cast<int>(pr) : m_unit) * 256 + static_cast<int>(rank) * 128;
-        const int n0 = (tile % p.num_n_blk) * BN + static_cast<int>(rank) * (BN / 2);
+        const int n0 = (tile % p.num_n_blk) * BN + (is_half ? ((w - p.half_from) & 1) * (BN / 2) + static_cast<int>(rank) * (BN / 4)
+                                                             : static_cast<int>(rank) * (BN / 2));
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
         const uint16_t mc_mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));  // same role, both pairs
@@ -799,12 +807,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (leader) {
       // the whole warp runs the loop (uniform operands, see ptx::elect_one); one elected lane issues
       const bool issue = ptx::elect_one();
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_full = ptx::umma_idesc_bf16(256, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_half = ptx::umma_idesc_bf16(256, BN / 2, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0;; ++it) {
         const int w = next_work(it);
         if (w < 0) break;
+        const uint32_t idesc = w >= p.half_from ? idesc_half : idesc_full;
         const int split = w % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blk, kb0 + p.kb_per_split);
@@ -854,14 +864,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int it = 0;; ++it) {
       const int w = next_work(it);
       if (w < 0) break;
-      const int tile = w / p.splits;
+      const bool is_half = w >= p.half_from;
+      const int tile = is_half ? p.half_from + ((w - p.half_from) >> 1) : w / p.splits;
       const int m_unit = tile / p.num_n_blk;
       const int m0 = (QUAD ? 2 * m_unit + static_cast<int>(pr) : m_unit) * 256 + static_cast<int>(rank) * 128;
       const int n_blk = tile % p.num_n_blk;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row = m0 + quarter * 32 + lane;
-      const int col_base = n_blk * BN + half * COLS_PER_WARP;
+      // half tile: accumulator columns [0, BN / 2) hold output columns n_blk BN + (w & 1) BN / 2 + ...; the warps of column
+      // groups 2 and 3 have nothing to store (their column base is pushed past N: every store / load below clips itself)
+      const int col_base = !is_half ? n_blk * BN + half * COLS_PER_WARP
+                                    : (2 * half < kNumEpiWarps / 4 ? n_blk * BN + ((w - p.half_from) & 1) * (BN / 2) + half * COLS_PER_WARP
+                                                                   : p.N + 32);
       constexpr int NCH = COLS_PER_WARP / 32;
       // auxiliary operands are requested before the accumulator wait (their DRAM latency hides behind the main loop)
       AuxChunk<EPI> aux[NCH];
@@ -1225,7 +1240,22 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
     p.wide = ok ? 1 : 0;
   }
 
-  const long long total = static_cast<long long>(num_m_units) * num_n_blk * splits;
+  long long total = static_cast<long long>(num_m_units) * num_n_blk * splits;
+  p.half_from = 0x7fffffff;
+  p.half_extra = 0;
+  if (pair && !quad && splits == 1 && epi != ABCGPT_EPI_F32_RED && p.sched == nullptr) {
+    // half tiles for a short last round of the static schedule (see gemm2_kernel); ABCGPT_GEMM_HALF_TILES=0 switches them off
+    static const bool on = [] {
+      const char* e = getenv("ABCGPT_GEMM_HALF_TILES");
+      return e == nullptr || e[0] != '0';
+    }();
+    const long long r = total % units;
+    if (on && total > units && r > 0 && 2 * r <= units && total + r < 0x7fffffff) {
+      p.half_from = static_cast<int>(total - r);
+      p.half_extra = static_cast<int>(r);
+      total += r;
+    }
+  }
   if (pair) return dispatch_major2(a_mn, b_mn, epi, tmA, tmB, p, total, quad, stream);
   const int grid = static_cast<int>(total < sms ? total : sms);
   if (bn == 256) return dispatch_major<256>(a_mn, b_mn, epi, tmA, tmB, p, grid, stream);

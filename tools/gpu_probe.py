@@ -374,6 +374,13 @@ def build_cases():
     cases["gemm2_gelu_tanh"] = lambda: case_gemm("gemm2_gelu_tanh", 1024, 1536, 384, False, False, E.EPI_GELU, 512, timing=False, tanh=True)
     cases["gemm2_dgelu_tanh"] = lambda: case_gemm("gemm2_dgelu_tanh", 1024, 1536, 384, False, True, E.EPI_DGELU, 512, timing=False, tanh=True)
     cases["gemm2_dgelu"] = lambda: case_gemm("gemm2_dgelu", 1024, 1536, 384, False, True, E.EPI_DGELU, 512, timing=False)
+    # half tiles of the pair kernel (a short last round of the static schedule is issued as 256 x 128 work items): 10 x 8 = 80 tiles
+    # on 74 pairs -> the last 6 tiles become 12 half items, including the ragged M / N edges; every epilogue and operand form
+    cases["gemm2_half_nt"] = lambda: case_gemm("gemm2_half_nt", 2500, 2000, 192, False, False, E.EPI_BF16, 512, timing=False)
+    cases["gemm2_half_nn"] = lambda: case_gemm("gemm2_half_nn", 2500, 2000, 192, False, True, E.EPI_BF16, 512, timing=False)
+    cases["gemm2_half_gelu"] = lambda: case_gemm("gemm2_half_gelu", 2560, 2048, 128, False, False, E.EPI_GELU, 512, timing=False)
+    cases["gemm2_half_dgelu"] = lambda: case_gemm("gemm2_half_dgelu", 2500, 2000, 128, False, True, E.EPI_DGELU, 512, timing=False)
+    cases["gemm2_half_resid"] = lambda: case_gemm("gemm2_half_resid", 2500, 2000, 192, False, False, E.EPI_RESID, 512, timing=False)
     cases["gemm_nt_ragged"] = lambda: case_gemm("gemm_nt_ragged", 200, 96, 136, False, False, E.EPI_BF16, 128, timing=False)
     cases["gemm_nt_f32"] = lambda: case_gemm("gemm_nt_f32", 256, 256, 768, False, False, E.EPI_F32, 256, timing=False)
     cases["gemm_gelu"] = lambda: case_gemm("gemm_gelu", 512, 1536, 384, False, False, E.EPI_GELU, 0, timing=False)
