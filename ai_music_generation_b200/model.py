@@ -249,7 +249,7 @@ class GPT(nn.Module):
         self._bufs = {}
         self._shadow_fresh = False
         self._pending_clip = None
-        self._plan_cache_enabled = True
+        self._plan_cache_enabled = os.environ.get("ABCGPT_PLAN_CACHE", "1") != "0"   # "0": derive every launch afresh (A/B runs)
         # weight-gradient GEMMs on a second stream for steps made of short kernels (see _backward_plan_impl)
         self._wgrad_side = os.environ.get("ABCGPT_WGRAD_SIDE", "auto")   # "0" / "1" force it off / on
         self._next_dropout_seed = None  # tests / reproducibility: force the seed of the next training forward
@@ -377,6 +377,14 @@ class GPT(nn.Module):
     # step) and costs when every kernel fills the GPU for 25-400 us (GPT-2-small shape at 32 k tokens: -1.8 %), see DESIGN 4.5
     _PDL_MAX_WORK = 8 * 1024 * 1024   # tokens x n_embd
 
+    @staticmethod
+    def _store_plan(bufs, plan_key, keys, p_drop):
+        """Keep a freshly recorded plan; with dropout on it is only reusable if its key sites could be identified."""
+        plan = ops.end_record()
+        patches = ops.key_patches(plan, keys) if p_drop > 0.0 else []
+        if patches is not None:
+            bufs.plans[plan_key] = (plan, patches)
+
     def _forward_plan(self, idx, targets, keep_activations, embeds=None, first=None, want_hidden=False):
         src = idx if idx is not None else embeds
         pdl = src.shape[0] * src.shape[1] * self.config.n_embd <= self._PDL_MAX_WORK
@@ -431,16 +439,17 @@ class GPT(nn.Module):
         # Launch-plan cache: with dropout off every argument of every launch is static (arena views, per-shape buffers,
         # the stream), so the plan is recorded once and replayed; inputs are staged into static buffers.
         plan_key = None
-        if p_drop == 0.0 and self._plan_cache_enabled and embeds is None and first is None and not want_hidden:
+        if self._plan_cache_enabled and embeds is None and first is None and not want_hidden:
             bufs.idx.copy_(idx)
             idx = bufs.idx
             if targets is not None:
                 bufs.tgt.copy_(targets)
                 targets = bufs.tgt
-            plan_key = ("fwd", targets is not None, torch.cuda.current_stream().cuda_stream)
+            # with dropout on, the per-site keys are the only arguments that change between steps: patched at replay
+            plan_key = ("fwd", targets is not None, torch.cuda.current_stream().cuda_stream, p_drop)
             plan = bufs.plans.get(plan_key)
             if plan is not None:
-                ops.replay(plan)
+                ops.replay(plan[0], plan[1], keys)
                 return bufs
             ops.begin_record()
         if embeds is not None:
@@ -487,7 +496,7 @@ class GPT(nn.Module):
             a = bufs.lnf.view(B, T * C)[:, (T - 1) * C:]
             ops.gemm(a, wte_bf16, M=B, N=bufs.Vpad, K=C, epilogue=ops.EPI_BF16, out=bufs.last_logits)
         if plan_key is not None:
-            bufs.plans[plan_key] = ops.end_record()
+            self._store_plan(bufs, plan_key, keys, p_drop)
         return bufs
 
     def _backward_plan_impl(self, bufs, idx, targets, grad_loss, drop, d_hidden=None, mode=0):
@@ -518,12 +527,12 @@ class GPT(nn.Module):
         if (self._wgrad_side == "1" or (self._wgrad_side == "auto" and bufs.B * bufs.T * cfg.n_embd <= self._PDL_MAX_WORK)) and not ops.profiling():
             side = ops.side_stream()
         plan_key = None
-        if (p_drop == 0.0 and self._plan_cache_enabled and mode == 0 and d_hidden is None and targets is not None
+        if (self._plan_cache_enabled and mode == 0 and d_hidden is None and targets is not None
                 and targets.data_ptr() == bufs.tgt.data_ptr()):
-            plan_key = ("bwd", sync is not None, torch.cuda.current_stream().cuda_stream, side is not None)
+            plan_key = ("bwd", sync is not None, torch.cuda.current_stream().cuda_stream, side is not None, p_drop)
             plan = bufs.plans.get(plan_key)
             if plan is not None:
-                ops.replay(plan)
+                ops.replay(plan[0], plan[1], keys)
                 return
             ops.begin_record()
         wte, wte_bf16, dwte = top["wte"]
@@ -605,7 +614,7 @@ class GPT(nn.Module):
         if sync is not None:
             ops.record_callback(sync.backward_done)
         if plan_key is not None:
-            bufs.plans[plan_key] = ops.end_record()
+            self._store_plan(bufs, plan_key, keys, p_drop)
         return dx
 
     # ------------------------------------------------------------------------------------------------------

@@ -37,6 +37,28 @@ def end_record():
     return plan
 
 
+_KEYED = ("embed_fwd", "embed_bwd", "layernorm_fwd_resid", "layernorm_bwd", "attn_fwd", "attn_bwd", "gemm")
+
+
+def key_patches(plan, keys):
+    """Dropout sites of a recorded plan: [(entry index, site)] for every launch that carries a dropout key (their C signatures
+    all end `..., dropout_p, dropout_key, stream`).  The keys are the only arguments of a training plan that change from step to
+    step, so a plan recorded with one step's keys is replayed with the next step's (`replay(plan, patches, keys)`).  Returns None
+    when the sites cannot be told apart (two sites with the same 32-bit key)."""
+    if len(set(keys)) != len(keys):
+        return None
+    site_of = {k: i for i, k in enumerate(keys)}
+    out = []
+    for i, e in enumerate(plan):
+        if e[0] in _KEYED and float(e[3][-3]) > 0.0:
+            site = site_of.get(int(e[3][-2]))
+            if site is None:
+                return None
+            plan[i] = (e[0], e[1], e[2], list(e[3]), e[4])
+            out.append((i, site))
+    return out
+
+
 def set_pdl(on):
     """Programmatic dependent launch for the launches that follow (include/abcgpt.h: abcgpt_set_pdl)."""
     _C.lib().abcgpt_set_pdl(1 if on else 0)
@@ -75,8 +97,11 @@ def record_callback(fn):
     fn()
 
 
-def replay(plan):
+def replay(plan, patches=None, keys=None):
     global LAUNCHES
+    if patches:
+        for i, site in patches:
+            plan[i][3][-2] = keys[site]
     if _PROFILE is not None:  # instrumented pass: fall back to event-bracketed calls
         for e in plan:
             if e[0] == "py":
