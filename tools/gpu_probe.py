@@ -292,6 +292,25 @@ def case_ce(name, M, V, ldl):
     return res
 
 
+def case_colsum(name, M, N, timing=False):
+    """Bias gradient: out[n] += sum_m dy[m, n] (bf16 in, fp32 accumulate), on top of a non-zero `out` (gradient accumulation)."""
+    import torch
+    from ai_music_generation_b200 import ops
+    torch.manual_seed(0)
+    dy = torch.randn(M, N, device="cuda").bfloat16()
+    out = torch.full((N,), 0.5, device="cuda")
+    ops.colsum_bf16(dy, out)
+    torch.cuda.synchronize()
+    ref = 0.5 + dy.double().sum(0)
+    err = (out.double() - ref).abs().max().item()
+    res = {"case": name, "max_abs": err, "ok": err <= 1e-3 * math.sqrt(M)}
+    if timing and res["ok"]:
+        ms = _timeit(lambda: ops.colsum_bf16(dy, out))
+        res["ms"] = ms
+        res["tb_per_s"] = M * N * 2 / ms / 1e9
+    return res
+
+
 def case_adamw(name, n):
     import torch
     from ai_music_generation_b200 import ops
@@ -424,6 +443,9 @@ def build_cases():
     cases["ln_resid_1000_bias"] = lambda: case_layernorm_resid("ln_resid_1000_bias", 1000, 1000, True)
     cases["ce_95"] = lambda: case_ce("ce_95", 32768, 95, 128)
     cases["ce_50304"] = lambda: case_ce("ce_50304", 512, 50304, 50304)
+    cases["colsum_768"] = lambda: case_colsum("colsum_768", 5000, 768)
+    cases["colsum_narrow_130"] = lambda: case_colsum("colsum_narrow_130", 3001, 130)   # N % 8 != 0: the 4-byte-per-lane kernel
+    cases["colsum_perf_cfg4"] = lambda: case_colsum("colsum_perf_cfg4", 262144, 3072, timing=True)
     cases["adamw"] = lambda: case_adamw("adamw", 85813248 // 8 + 3)
     cases["adamw_full"] = lambda: case_adamw("adamw_full", 85813248)
     cases["embed"] = lambda: case_embed("embed", 32, 1024, 768, 95)
