@@ -383,10 +383,10 @@ def main():
                      "avg_launch_ms": gemm_ms / gemm_calls, "flops_per_step": gemm_fl,
                      # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) are NOT measured by this run: the
                      # figure is the launch-weighted mean over the twelve GEMM launches of a block at the cfg3 shapes, seven
-                     # roles captured by ncu (profiles/r2_ncu_gemm.md), the other five from their operand sizes (the captured
+                     # roles captured by ncu (profiles/r2b_ncu_gemm.md), the other five from their operand sizes (the captured
                      # roles' traffic equals their algorithmic bytes); null for other workloads
                      "traffic": 240e6 if args.workload == "cfg3" else None,
-                     "traffic_source": "profiles/r2_ncu_gemm.md (ncu capture per role, launch-weighted mean; not re-measured per run)"
+                     "traffic_source": "profiles/r2b_ncu_gemm.md (ncu capture per role, launch-weighted mean; not re-measured per run)"
                      if args.workload == "cfg3" else None},
         "kernel_breakdown": fam,
     }

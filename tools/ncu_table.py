@@ -12,6 +12,9 @@ raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], captu
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, launches = rows[0], rows[1], rows[2:]
 idx = {h: i for i, h in enumerate(hdr)}
+# torch's own helper kernels (random fills, copies of the driver script) are not part of the product: dropped unless --all
+if "--all" not in sys.argv:
+    launches = [r for r in launches if "at::" not in r[idx["Kernel Name"]]]
 METRICS = [("gpu__time_duration.sum", "duration"), ("sm__cycles_elapsed.avg.per_second", "SM clock"),
            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active"),
            ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe"),
