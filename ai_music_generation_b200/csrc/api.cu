@@ -215,4 +215,13 @@ int abcgpt_event_wait(int slot, void* stream) {
   return 0;
 }
 
+/* Data-parallel gradient exchange over NVLink-switch multicast memory, fused with the clip norm (csrc/nvls.cu) */
+int abcgpt_nvls_allreduce_sumsq(void* grad_multicast, int64_t n, int rank, int world, float scale, void* partials_multicast,
+                                int blocks_per_rank, int threads_per_block, void* stream) {
+  return nvls_allreduce_sumsq(grad_multicast, n, rank, world, scale, partials_multicast, blocks_per_rank, threads_per_block, S(stream));
+}
+int abcgpt_sumsq_partials(const float* partials, int nparts, float* out, void* stream) {
+  return sumsq_partials(partials, nparts, out, S(stream));
+}
+
 }  // extern "C"

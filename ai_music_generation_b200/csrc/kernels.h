@@ -50,6 +50,9 @@ int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream);
 int attn_decode(const void* cache, void* out, int B, int Tmax, int n_keys, int H, cudaStream_t stream);
 int sample_batch(const void* data, int token_bytes, long long n_tokens, const int64_t* ix, int64_t* x, int64_t* y, int B, int T,
                  cudaStream_t stream);
+int nvls_allreduce_sumsq(void* grad_mc, long long n, int rank, int world, float scale, void* partials_mc, int blocks_per_rank,
+                         int threads, cudaStream_t stream);
+int sumsq_partials(const float* partials, int nparts, float* out, cudaStream_t stream);
 int colsum_bf16(const void* dy, long long ld, int M, int N, float* out, cudaStream_t stream);
 int argmax_rows(const void* logits, long long ldl, int V, int64_t* out, long long out_stride, int B,
                 cudaStream_t stream);

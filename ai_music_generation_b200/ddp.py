@@ -7,11 +7,23 @@ first); each bucket's all-reduce (average) is enqueued on a side stream as soon 
 has been launched, overlapping NCCL over NVLink with the remaining backward.  The embedding / lm_head tensor
 and the 1-D parameters finish last and form the final bucket.  `wait()` makes the compute stream wait for the
 outstanding collectives (device-side; no host sync) before clip / AdamW.
+
+NVLS mode (the default when the GPUs share a multicast-capable NVLink switch; `DDP(..., nvls=False)` or ABCGPT_DDP_NVLS=0 keeps
+NCCL): the gradient arena lives in symmetric multicast memory and every bucket is exchanged by ONE kernel of ours — each rank
+reduces its 1/world share through the switch (multimem.ld_reduce), multicasts the mean into every replica and, in the same
+pass, the partial sums of squares that clip_grad_norm_ needs (csrc/nvls.cu, include/abcgpt.h abcgpt_nvls_allreduce_sumsq).
+The kernel runs in 128-thread CTAs that share SMs with the backward's persistent GEMM CTAs instead of taking SMs away from
+their static tile schedule (what an NCCL kernel does), and the separate norm pass over the arena disappears.
 """
 from __future__ import annotations
 
+import os
+import warnings
+
 import torch
 import torch.distributed as dist
+
+from . import ops
 
 
 def plan_buckets(layer_ranges, head_range, tail_range, bucket_elems, extra_ranges=()):
@@ -40,8 +52,10 @@ def plan_buckets(layer_ranges, head_range, tail_range, bucket_elems, extra_range
 
 class GradSync:
     def __init__(self, grad_flat, layer_ranges, head_range, tail_range, process_group=None, bucket_mb=64.0,
-                 extra_ranges=(), defer_final=False):
+                 extra_ranges=(), defer_final=False, nvls=None):
         self.grad = grad_flat
+        self.nvls = nvls           # symmetric-memory state of the NVLS mode (see nvls_setup) or None: NCCL buckets
+        self.norm_fresh = False    # NVLS: the partial-norm table describes the gradients currently in the arena
         self.group = process_group
         self.world = dist.get_world_size(process_group)
         self.buckets = plan_buckets(layer_ranges, head_range, tail_range, int(bucket_mb * 1024 * 1024 / 4), extra_ranges)
@@ -52,7 +66,8 @@ class GradSync:
         for b in self.buckets:
             self._by_trigger.setdefault(b[0], []).append(b)
         self.cuda = grad_flat.is_cuda
-        self.comm_stream = torch.cuda.Stream(device=grad_flat.device) if self.cuda else None
+        # high priority: the exchange kernels are tiny (NVLS) or latency-bound (NCCL) and should not queue behind compute CTAs
+        self.comm_stream = torch.cuda.Stream(device=grad_flat.device, priority=-1 if nvls is not None else 0) if self.cuda else None
         self._pending = []
         self.launched = []  # (lo, hi) in launch order, for tests
 
@@ -62,7 +77,16 @@ class GradSync:
         self.launched.append((lo, hi))
         if self.world == 1:
             return
-        if self.cuda:
+        if self.nvls is not None:
+            # NVLS, overlapped: the bucket's exchange runs on the communication stream as soon as the bucket's last wgrad has
+            # been enqueued, in 128-thread CTAs that share SMs with the backward's persistent kernels (csrc/nvls.cu)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ready)
+                self._nvls_exchange(lo, hi, self.buckets.index(bucket), self.nvls["blocks"], self.nvls["threads"])
+            self.nvls["dirty"] = True
+        elif self.cuda:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
@@ -73,7 +97,19 @@ class GradSync:
             dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
             view.div_(self.world)
 
+    def _nvls_exchange(self, lo, hi, slot, blocks, threads):
+        """On the current stream: barrier (every rank has finished writing this range of its arena), the fused reduce +
+        multicast + norm-partials kernel on this rank's share of the range, barrier (every share has landed in every replica)."""
+        nv = self.nvls
+        hdl = nv["hdl"]
+        hdl.barrier(channel=0)
+        ops.nvls_allreduce_sumsq(hdl.multicast_ptr + 4 * lo, hi - lo, hdl.rank, hdl.world_size,
+                                 nv["thdl"].multicast_ptr + 4 * slot * hdl.world_size * blocks, blocks, threads)
+        hdl.barrier(channel=0)
+
     def layer_done(self, li):
+        if self.nvls is not None and not self.nvls["overlap"]:
+            return   # one exchange of the whole arena at the end of the backward (finalize)
         for b in self._by_trigger.get(li, ()):
             self._launch(b)
 
@@ -87,11 +123,36 @@ class GradSync:
         `torch.nn.utils.clip_grad_norm_(model.parameters(), ...)` (nanoGPT/train.py:350-352), `scaler.step`, a gradient
         read — therefore sees fully reduced gradients, exactly as with torch DDP.  Nothing else is queued behind the
         backward at this point, so the join costs no overlap."""
-        for b in self._by_trigger.get(-1, ()):
-            self._launch(b)
+        if self.nvls is not None and not self.nvls["overlap"]:
+            if self.world > 1:
+                self._nvls_exchange(0, self.grad.numel(), 0, max(1, 1024 // self.world), 512)   # one launch, the GPU to itself
+            self.launched.append((0, self.grad.numel()))
+        else:
+            for b in self._by_trigger.get(-1, ()):
+                self._launch(b)
         self._join()
+        if self.nvls is not None:
+            self.nvls["version"] = self.grad._version
+            self.norm_fresh = True
+
+    def fused_sumsq(self, out):
+        """NVLS mode: adds the squared norm of the exchanged gradients to out[0] from the partial table (no pass over the
+        arena); False when the table does not describe the arena's current contents (then the caller runs its own pass)."""
+        nv = self.nvls
+        if nv is None or not self.norm_fresh or nv.get("version") != self.grad._version:
+            return False
+        nparts = (len(self.buckets) * nv["blocks"] if nv["overlap"] else max(1, 1024 // self.world)) * self.world
+        ops.sumsq_partials(nv["table"], nparts, out)
+        return True
 
     def _join(self):
+        if self.nvls is not None:
+            if self.nvls.get("dirty"):
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+                torch.cuda.current_stream().wait_event(done)
+                self.nvls["dirty"] = False
+            return
         for w in self._pending:
             w.wait()  # NCCL: the current stream waits for the collective; the host does not block
         self._pending = []
@@ -101,9 +162,58 @@ class GradSync:
         self.launched = []
 
 
-def attach_grad_sync(m, process_group=None, bucket_mb=64.0, defer_final=False):
+def nvls_requested(flag=None):
+    """Default: try the NVLS exchange whenever there is more than one rank (nvls_setup falls back to NCCL with a warning when the
+    GPUs have no multicast memory); ABCGPT_DDP_NVLS=0 forces the NCCL buckets.  MEASURED (cfg3, one box each, profiles/r2b_nvls.md):
+    8 GPUs 25.80 -> 25.15 / 25.25 ms per step, 2 GPUs 25.32 -> 25.03 ms."""
+    if flag is None:
+        return os.environ.get("ABCGPT_DDP_NVLS", "1") != "0"
+    return bool(flag)
+
+
+def nvls_setup(m, process_group=None):
+    """Moves the module's gradient arena into symmetric multicast memory (torch.distributed._symmetric_memory: allocation and
+    handle exchange only) and allocates the partial-norm table.  Returns the state dict GradSync keeps, or None (with one
+    warning) when the GPUs do not share a multicast-capable NVLink switch / the allocation fails: the caller falls back to NCCL."""
+    a = m._arena
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        group = process_group if process_group is not None else dist.group.WORLD
+        dev = a["flat"].device
+        g = symm_mem.empty(a["total"], dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(g, group)
+        table = symm_mem.empty(65536, dtype=torch.float32, device=dev)   # [buckets x world x blocks] partial sums of squares
+        thdl = symm_mem.rendezvous(table, group)
+        ok = torch.tensor([1 if (hdl.multicast_ptr and thdl.multicast_ptr and a["total"] % 4 == 0) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)   # all ranks take the same path
+        if int(ok.item()) == 0:
+            raise RuntimeError("no multicast address for the symmetric allocation")
+    except Exception as e:  # noqa: BLE001 - any failure here means "use NCCL"
+        warnings.warn(f"NVLS gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce buckets")
+        return None
+    g.zero_()
+    table.zero_()
+    if a["grad"] is not None:
+        g.copy_(a["grad"])
+    a["grad"] = g
+    for p, o in zip(a["params"], a["offs"]):   # existing .grad views follow the arena
+        if p.grad is not None:
+            p.grad = g[o:o + p.numel()].view(p.shape)
+    m._bufs = {}   # recorded launch plans hold the old arena's pointers
+    # overlap (default): bucket by bucket beside the backward, `blocks` CTAs of `threads` threads per launch — one small CTA per SM
+    # fits next to a persistent GEMM CTA; ABCGPT_NVLS_OVERLAP=0: one exchange of the whole arena after the backward
+    return {"hdl": hdl, "thdl": thdl, "table": table, "overlap": os.environ.get("ABCGPT_NVLS_OVERLAP", "1") != "0",
+            "blocks": int(os.environ.get("ABCGPT_NVLS_BLOCKS", "148")), "threads": int(os.environ.get("ABCGPT_NVLS_THREADS", "128"))}
+
+
+def attach_grad_sync(m, process_group=None, bucket_mb=64.0, defer_final=False, nvls=False):
     """Builds the GradSync of one GPT-shaped module over its flat gradient arena and stores it in m._grad_sync."""
     m._ensure_device_state()
+    nv = None
+    if nvls and m._arena["flat"].is_cuda and dist.get_world_size(process_group) > 1:
+        nv = nvls_setup(m, process_group)
+    if nv is not None:   # per-layer buckets: the last exchange (the exposed one) stays short; measured 25.15 -> 25.03 ms at N = 2
+        bucket_mb = min(bucket_mb, float(os.environ.get("ABCGPT_NVLS_BUCKET_MB", "25")))
     a = m._arena
     names, offs, params = a["names"], a["offs"], a["params"]
     end = {n: o + ((p.numel() + 7) // 8) * 8 for n, o, p in zip(names, offs, params)}
@@ -116,18 +226,19 @@ def attach_grad_sync(m, process_group=None, bucket_mb=64.0, defer_final=False):
     extra = [(layer_ranges[-1][1], a["n_decay"])] if layer_ranges else []
     tail = (a["n_decay"], a["total"])
     m._grad_sync = GradSync(a["grad"], layer_ranges, head, tail, process_group, bucket_mb, extra_ranges=extra,
-                            defer_final=defer_final)
+                            defer_final=defer_final, nvls=nv)
     return m._grad_sync
 
 
 class DDP(torch.nn.Module):
     """Thin container with the two attributes the reference's training loop touches."""
 
-    def __init__(self, module, device_ids=None, process_group=None, bucket_mb=64.0):
+    def __init__(self, module, device_ids=None, process_group=None, bucket_mb=64.0, nvls=None):
         super().__init__()
         self.module = module
         self._process_group = process_group
         self._bucket_mb = bucket_mb
+        self._nvls = nvls_requested(nvls)
         self._sync_for = None
         if dist.is_initialized() and dist.get_world_size(process_group) > 1:
             flat = module._arena["flat"]
@@ -145,11 +256,10 @@ class DDP(torch.nn.Module):
     def _ensure_sync(self):
         m = self.module
         m._ensure_device_state()
-        key = m._arena["grad"].data_ptr()
-        if self._sync_for == key:
+        if self._sync_for == m._arena["grad"].data_ptr():
             return
-        attach_grad_sync(m, self._process_group, self._bucket_mb)
-        self._sync_for = key
+        attach_grad_sync(m, self._process_group, self._bucket_mb, nvls=self._nvls)
+        self._sync_for = m._arena["grad"].data_ptr()   # (the NVLS mode replaces the arena)
 
     def forward(self, *args, **kwargs):
         if dist.is_initialized():

@@ -521,6 +521,8 @@ class GPT(nn.Module):
         gl = bufs.gl
         tflat = targets.contiguous().view(-1) if targets is not None else None
         sync = self._grad_sync if (self._grad_sync is not None and self.require_backward_grad_sync) else None
+        if self._grad_sync is not None:
+            self._grad_sync.norm_fresh = False   # the arena is about to change; a fused exchange at the end sets it again
         # like programmatic dependent launch, the second stream pays where kernels are short (baby GPT 2.66 -> 2.57 ms per step);
         # at the GPT-2-small shape with 32 k tokens the step is energy-bound and it measured neutral (24.54 / 24.61 vs 24.67 / 24.65 ms)
         side = None
@@ -756,7 +758,8 @@ class GPT(nn.Module):
             self._grad_sync.wait()
         ss = a.setdefault("sumsq", torch.zeros(1, device=a["flat"].device, dtype=torch.float32))
         ss.zero_()
-        ops.sumsq(a["grad"], ss)
+        if self._grad_sync is None or not self._grad_sync.fused_sumsq(ss):   # NVLS exchange: the norm came with the gradients
+            ops.sumsq(a["grad"], ss)
         self._pending_clip = (ss, float(max_norm))
         return ss.sqrt().view(())
 

@@ -92,9 +92,15 @@ def event_wait(slot, stream=None):
 
 def record_callback(fn):
     """Interleave a Python callback (e.g. DDP bucket launch) with the recorded launches; runs now and on every replay."""
-    if _RECORD is not None:
-        _RECORD.append(("py", fn))
-    fn()
+    global _RECORD
+    rec = _RECORD
+    if rec is not None:
+        rec.append(("py", fn))
+    _RECORD = None   # launches made BY the callback belong to the callback (it runs again on every replay), not to the plan
+    try:
+        fn()
+    finally:
+        _RECORD = rec
 
 
 def replay(plan, patches=None, keys=None):
@@ -388,6 +394,16 @@ def sample_topk(logits, V, out, temperature, top_k, seed, counter, out_stride=1)
     B, ldl = logits.shape[0], logits.stride(0)
     _call("sample_topk", 1, (B, V), _C.lib().abcgpt_sample_topk, logits.data_ptr(), ldl, V, float(temperature),
           int(top_k) if top_k is not None else 0, seed.data_ptr(), int(counter), out.data_ptr(), out_stride, B, _stream())
+
+
+def nvls_allreduce_sumsq(grad_mc_ptr, n, rank, world, partials_mc_ptr, blocks_per_rank, threads=512):
+    """include/abcgpt.h abcgpt_nvls_allreduce_sumsq: mean of the replicas' gradient arenas + norm partials, over multicast memory."""
+    _call("nvls_allreduce_sumsq", 1, (n, world), _C.lib().abcgpt_nvls_allreduce_sumsq, int(grad_mc_ptr), int(n), int(rank), int(world),
+          1.0 / world, int(partials_mc_ptr), int(blocks_per_rank), int(threads), _stream())
+
+
+def sumsq_partials(partials, nparts, out):
+    _call("sumsq_partials", 1, (nparts,), _C.lib().abcgpt_sumsq_partials, partials.data_ptr(), int(nparts), out.data_ptr(), _stream())
 
 
 def colsum_bf16(dy, out):

@@ -367,7 +367,10 @@ def main():
         "data": "synthetic",
         "config": {"workload": wl["name"], "global_batch": world * B, "seq_len": T, "parallelism": f"dp{world}",
                    "l2_note": "per-step working set ~11 GB of activations >> 126 MB L2; no explicit flush",
-                   "optimizer": "fused clip_grad_norm_(1.0) + AdamW every step, grad accumulation 1", "dropout": args.dropout},
+                   "optimizer": "fused clip_grad_norm_(1.0) + AdamW every step, grad accumulation 1", "dropout": args.dropout,
+                   "grad_exchange": ("none (1 GPU)" if world == 1 else
+                                     ("nvls: one multimem.ld_reduce / multimem.st kernel + norm partials (csrc/nvls.cu)"
+                                      if getattr(model._grad_sync, "nvls", None) is not None else "nccl all-reduce buckets overlapped with the backward"))},
         "mfu": {"flops_per_token": fpt, "per_gpu_tflops": value / world * fpt / 1e12,
                 "of_nominal_2250": value / world * fpt / 2.25e15,
                 "of_measured_burst": value / world * fpt / (pk["burst"] * 1e12),

@@ -140,15 +140,14 @@ def stock_train_loop_case(rank, world, dev):
     print(f"DDP_STOCK_LOOP_OK rank {rank} rel {rel:.2e} norms {n_ddp[0]:.4f}/{n_ref[0]:.4f} eval {out['val'].item():.5f}", flush=True)
 
 
-def main():
-    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+def gpt_case(rank, world, dev, nvls):
+    """DDP gradient == concatenated-batch gradient, the accumulation toggle, replicas bitwise in sync after optimizer steps.
+    nvls=True: the fused NVLink-switch exchange (csrc/nvls.cu) instead of NCCL buckets — same checks, plus the norm that
+    comes with the gradients must be the norm of the arena."""
     cfg = dict(block_size=128, vocab_size=95, n_layer=4, n_head=2, n_embd=128, dropout=0.0, bias=False)
     torch.manual_seed(1337 + rank)  # different init per rank: the DDP constructor must broadcast rank 0's parameters
     model = GPT(GPTConfig(**cfg)).to(dev).train()
-    ddp = DDP(model, bucket_mb=0.5)
+    ddp = DDP(model, bucket_mb=0.5, nvls=nvls)
     ref = GPT(GPTConfig(**cfg)).to(dev).train()
     ref.load_state_dict(model.state_dict())
     p0 = model._arena["flat"].clone()
@@ -163,6 +162,8 @@ def main():
     # two micro-steps: the first must NOT all-reduce
     ddp.require_backward_grad_sync = False
     _, l0 = ddp(X[rank * B:(rank + 1) * B].contiguous(), Y[rank * B:(rank + 1) * B].contiguous())
+    if nvls and model._grad_sync.nvls is None:
+        return False   # no multicast on this box: the wrapper fell back to NCCL (covered by the nvls=False run)
     (l0 / 2).backward()
     local_only = model._arena["grad"].clone()
     ddp.require_backward_grad_sync = True
@@ -178,7 +179,14 @@ def main():
     rel = ((got - want).norm() / want.norm()).item()
     assert rel < 2e-2, rel
     assert not torch.allclose(local_only * 2, got, rtol=1e-3, atol=1e-6), "first micro-step seems to have been all-reduced"
+    gathered = [torch.empty_like(got) for _ in range(world)]
+    dist.all_gather(gathered, got)
+    for other in gathered:
+        assert torch.equal(other, got), "exchanged gradients differ between ranks"
     norm = model.clip_grad_norm_(1.0)
+    if nvls:
+        assert model._grad_sync.norm_fresh, "the fused exchange did not leave a norm"
+        assert abs(norm.item() - got.double().norm().item()) <= 1e-4 * got.double().norm().item(), (norm.item(), got.norm().item())
     opt.step()
     opt.zero_grad(set_to_none=True)
     for _ in range(3):
@@ -192,7 +200,19 @@ def main():
     dist.all_gather(gathered, flat)
     for other in gathered:
         assert torch.equal(other, flat), "ranks diverged"
-    print(f"DDP_GPU_OK rank {rank} rel {rel:.2e} norm {norm.item():.4f} buckets {len(model._grad_sync.buckets)}", flush=True)
+    tag = "DDP_NVLS_OK" if nvls else "DDP_GPU_OK"
+    print(f"{tag} rank {rank} rel {rel:.2e} norm {norm.item():.4f} buckets {len(model._grad_sync.buckets)}", flush=True)
+    return True
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    gpt_case(rank, world, dev, nvls=False)
+    if not gpt_case(rank, world, dev, nvls=True):
+        print(f"DDP_NVLS_SKIPPED rank {rank} (no multicast memory on this box)", flush=True)
     tunesformer_case(rank, world, dev)
     stock_train_loop_case(rank, world, dev)
     dist.destroy_process_group()
