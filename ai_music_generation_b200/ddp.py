@@ -70,6 +70,25 @@ class GradSync:
         self.comm_stream = torch.cuda.Stream(device=grad_flat.device, priority=-1 if nvls is not None else 0) if self.cuda else None
         self._pending = []
         self.launched = []  # (lo, hi) in launch order, for tests
+        if nvls is not None:
+            # every exchange costs a pair of device-side barriers, and the ones released at the END of the backward are exposed:
+            # the lowest layer group joins the ranges around it (head | group | ... and patch embedding | 1-D tail are adjacent in
+            # the arena), so the backward ends with one or two launches instead of four
+            last = [b for b in self.buckets if b[0] <= 0]
+            rest = [b for b in self.buckets if b[0] > 0]
+            merged = []
+            for _, lo, hi in sorted(last, key=lambda b: b[1]):
+                if merged and merged[-1][2] == lo:
+                    merged[-1] = (-1, merged[-1][1], hi)
+                else:
+                    merged.append((-1, lo, hi))
+            self.buckets = rest + merged
+            self._by_trigger = {}
+            for b in self.buckets:
+                self._by_trigger.setdefault(b[0], []).append(b)
+            # one table slot per (bucket, rank, block): many-layer models get fewer blocks per launch
+            cap = nvls["table"].numel() // max(1, len(self.buckets) * self.world)
+            nvls["blocks"] = max(1, min(nvls["blocks"], cap))
 
     def _launch(self, bucket):
         _, lo, hi = bucket
@@ -163,12 +182,17 @@ class GradSync:
 
 
 def nvls_requested(flag=None):
-    """Default: try the NVLS exchange whenever there is more than one rank (nvls_setup falls back to NCCL with a warning when the
-    GPUs have no multicast memory); ABCGPT_DDP_NVLS=0 forces the NCCL buckets.  MEASURED (cfg3, one box each, profiles/r2b_nvls.md):
+    """Default ("auto"): the NVLS exchange for gradient arenas of at least 128 MB whenever there is more than one rank (nvls_setup
+    falls back to NCCL with a warning when the GPUs have no multicast memory); ABCGPT_DDP_NVLS=0 / 1 force NCCL / NVLS.  MEASURED (cfg3, one box each, profiles/r2b_nvls.md):
     8 GPUs 25.80 -> 25.15 / 25.25 ms per step, 2 GPUs 25.32 -> 25.03 ms."""
     if flag is None:
-        return os.environ.get("ABCGPT_DDP_NVLS", "1") != "0"
+        e = os.environ.get("ABCGPT_DDP_NVLS", "auto")
+        return "auto" if e == "auto" else e != "0"
     return bool(flag)
+
+
+NVLS_AUTO_MIN_BYTES = 128 << 20   # "auto": arenas below this stay on NCCL (baby GPT, 43 MB, 2 GPUs: 2.67 ms NCCL vs 2.73 ms NVLS —
+                                  # a handful of small exchanges, each between two device-side barriers, against one all-reduce)
 
 
 def nvls_setup(m, process_group=None):
@@ -210,6 +234,8 @@ def attach_grad_sync(m, process_group=None, bucket_mb=64.0, defer_final=False, n
     """Builds the GradSync of one GPT-shaped module over its flat gradient arena and stores it in m._grad_sync."""
     m._ensure_device_state()
     nv = None
+    if nvls == "auto":
+        nvls = m._arena["total"] * 4 >= NVLS_AUTO_MIN_BYTES
     if nvls and m._arena["flat"].is_cuda and dist.get_world_size(process_group) > 1:
         nv = nvls_setup(m, process_group)
     if nv is not None:   # per-layer buckets: the last exchange (the exposed one) stays short; measured 25.15 -> 25.03 ms at N = 2
