@@ -76,7 +76,7 @@ def stock_train_loop_case(rank, world, dev):
     ref = GPT(GPTConfig(**cfg)).to(dev).train()
     ref.load_state_dict(model.state_dict())
     raw_model = model
-    model = DDP(model, device_ids=[dev.index], bucket_mb=0.25)
+    model = DDP(model, device_ids=[dev.index], bucket_mb=0.25, nvls=True)   # NVLS exchange where the box has multicast memory (else NCCL)
     g = torch.Generator().manual_seed(21)
     B, accum, iters, grad_clip = 2, 2, 4, 1.0
     data = [(torch.randint(95, (world * B, 128), generator=g), torch.randint(95, (world * B, 128), generator=g))
