@@ -55,6 +55,7 @@ _SIGNATURES = {
     "abcgpt_event_wait": (c_int, [c_int, _P]),
     "abcgpt_nvls_allreduce_sumsq": (c_int, [_P, c_int64, c_int, c_int, c_float, _P, c_int, c_int, _P]),
     "abcgpt_sumsq_partials": (c_int, [_P, c_int, _P, _P]),
+    "abcgpt_set_dynamic_tiles": (c_int, [c_int]),
     "abcgpt_argmax": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P]),
     "abcgpt_sample_topk": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, c_int64, _P, c_int64, c_int, _P]),
 }

@@ -23,6 +23,8 @@
 namespace abcgpt {
 
 unsigned long long* g_gemm_stats = nullptr;  // debug only: set through abcgpt_debug_gemm_stats
+bool g_dynamic_tiles = false;                // abcgpt_set_dynamic_tiles: ticket-based tile scheduler for the pair GEMM launches that follow
+void set_dynamic_tiles(bool on) { g_dynamic_tiles = on; }
 
 namespace {
 
@@ -1110,9 +1112,9 @@ int* sched_counter(cudaStream_t stream) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("ABCGPT_DYNAMIC_TILES");
-    enabled = (e != nullptr && e[0] == '1') ? 1 : 0;
+    enabled = (e == nullptr || e[0] == '\0') ? 2 : (e[0] == '1' ? 1 : 0);   // 2: not forced, the caller decides (set_dynamic_tiles)
   }
-  if (!enabled) return nullptr;
+  if (enabled == 0 || (enabled == 2 && !g_dynamic_tiles)) return nullptr;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(mu);

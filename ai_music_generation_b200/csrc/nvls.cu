@@ -40,8 +40,22 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
+// world == 1 (no switch involved: plain loads / stores through the same code path; used by the co-residency probe and by
+// single-rank process groups)
+template <bool MC>
+__device__ __forceinline__ float4 ld_sum(const float* p) {
+  if constexpr (MC) return mm_ld_reduce_add(p);
+  return *reinterpret_cast<const float4*>(p);
+}
+template <bool MC>
+__device__ __forceinline__ void st_all(float* p, const float4& v) {
+  if constexpr (MC) mm_st(p, v);
+  else *reinterpret_cast<float4*>(p) = v;
+}
+
 constexpr int kUnroll = 4;   // 16-byte switch reductions in flight per thread (~3 us round trip: 128 blocks x 512 threads x 64 B = 4 MB)
 
+template <bool MC>
 __global__ void __launch_bounds__(512)
 nvls_allreduce_sumsq_kernel(float* __restrict__ grad_mc, long long lo4, long long hi4, float scale, float* __restrict__ partials_mc,
                             int slot0) {
@@ -52,19 +66,19 @@ nvls_allreduce_sumsq_kernel(float* __restrict__ grad_mc, long long lo4, long lon
   for (; i + (kUnroll - 1) * stride < hi4; i += kUnroll * stride) {
     float4 v[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) v[u] = mm_ld_reduce_add(grad_mc + 4 * (i + u * stride));
+    for (int u = 0; u < kUnroll; ++u) v[u] = ld_sum<MC>(grad_mc + 4 * (i + u * stride));
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       v[u].x *= scale; v[u].y *= scale; v[u].z *= scale; v[u].w *= scale;
       s += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
-      mm_st(grad_mc + 4 * (i + u * stride), v[u]);
+      st_all<MC>(grad_mc + 4 * (i + u * stride), v[u]);
     }
   }
   for (; i < hi4; i += stride) {
-    float4 v = mm_ld_reduce_add(grad_mc + 4 * i);
+    float4 v = ld_sum<MC>(grad_mc + 4 * i);
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
     s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-    mm_st(grad_mc + 4 * i, v);
+    st_all<MC>(grad_mc + 4 * i, v);
   }
   s = warp_sum_f(s);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -72,7 +86,10 @@ nvls_allreduce_sumsq_kernel(float* __restrict__ grad_mc, long long lo4, long lon
   if (threadIdx.x < 32) {
     s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
     s = warp_sum_f(s);
-    if (threadIdx.x == 0) mm_st1(partials_mc + slot0 + blockIdx.x, s);   // this block's share of the norm, to every rank's table
+    if (threadIdx.x == 0) {   // this block's share of the norm, to every rank's table
+      if constexpr (MC) mm_st1(partials_mc + slot0 + blockIdx.x, s);
+      else partials_mc[slot0 + blockIdx.x] = s;
+    }
   }
 }
 
@@ -105,8 +122,12 @@ int nvls_allreduce_sumsq(void* grad_mc, long long n, int rank, int world, float 
                    "nvls_allreduce_sumsq: multicast pointers must be 16-byte (arena) / 4-byte (table) aligned");
   const long long n4 = n / 4, per = (n4 + world - 1) / world;
   const long long lo = per * rank < n4 ? per * rank : n4, hi = lo + per < n4 ? lo + per : n4;
-  nvls_allreduce_sumsq_kernel<<<blocks_per_rank, threads, 0, stream>>>(reinterpret_cast<float*>(grad_mc), lo, hi, scale,
-                                                                   reinterpret_cast<float*>(partials_mc), rank * blocks_per_rank);
+  if (world == 1)
+    nvls_allreduce_sumsq_kernel<false><<<blocks_per_rank, threads, 0, stream>>>(reinterpret_cast<float*>(grad_mc), lo, hi, scale,
+                                                                            reinterpret_cast<float*>(partials_mc), 0);
+  else
+    nvls_allreduce_sumsq_kernel<true><<<blocks_per_rank, threads, 0, stream>>>(reinterpret_cast<float*>(grad_mc), lo, hi, scale,
+                                                                           reinterpret_cast<float*>(partials_mc), 0);
   return launch_status("nvls_allreduce_sumsq_kernel");
 }
 

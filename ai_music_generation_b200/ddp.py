@@ -88,7 +88,8 @@ class GradSync:
                 self._by_trigger.setdefault(b[0], []).append(b)
             # one table slot per (bucket, rank, block): many-layer models get fewer blocks per launch
             cap = nvls["table"].numel() // max(1, len(self.buckets) * self.world)
-            nvls["blocks"] = max(1, min(nvls["blocks"], cap))
+            nvls["bmax"] = max(1, min(296, cap))
+            nvls["blocks"] = max(1, min(nvls["blocks"], nvls["bmax"]))
 
     def _launch(self, bucket):
         _, lo, hi = bucket
@@ -103,7 +104,9 @@ class GradSync:
             ready.record(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ready)
-                self._nvls_exchange(lo, hi, self.buckets.index(bucket), self.nvls["blocks"], self.nvls["threads"])
+                final = bucket[0] < 0   # released when the backward has ended: nothing left to disturb, full-size launch
+                self._nvls_exchange(lo, hi, self.buckets.index(bucket), self.nvls["bmax"] if final else self.nvls["blocks"],
+                                    512 if final else self.nvls["threads"])
             self.nvls["dirty"] = True
         elif self.cuda:
             ready = torch.cuda.Event()
@@ -123,7 +126,7 @@ class GradSync:
         hdl = nv["hdl"]
         hdl.barrier(channel=0)
         ops.nvls_allreduce_sumsq(hdl.multicast_ptr + 4 * lo, hi - lo, hdl.rank, hdl.world_size,
-                                 nv["thdl"].multicast_ptr + 4 * slot * hdl.world_size * blocks, blocks, threads)
+                                 nv["thdl"].multicast_ptr + 4 * (slot * hdl.world_size + hdl.rank) * nv["bmax"], blocks, threads)
         hdl.barrier(channel=0)
 
     def layer_done(self, li):
@@ -144,7 +147,7 @@ class GradSync:
         backward at this point, so the join costs no overlap."""
         if self.nvls is not None and not self.nvls["overlap"]:
             if self.world > 1:
-                self._nvls_exchange(0, self.grad.numel(), 0, max(1, 1024 // self.world), 512)   # one launch, the GPU to itself
+                self._nvls_exchange(0, self.grad.numel(), 0, self.nvls["bmax"], 512)   # one launch, the GPU to itself
             self.launched.append((0, self.grad.numel()))
         else:
             for b in self._by_trigger.get(-1, ()):
@@ -160,8 +163,8 @@ class GradSync:
         nv = self.nvls
         if nv is None or not self.norm_fresh or nv.get("version") != self.grad._version:
             return False
-        nparts = (len(self.buckets) * nv["blocks"] if nv["overlap"] else max(1, 1024 // self.world)) * self.world
-        ops.sumsq_partials(nv["table"], nparts, out)
+        # table layout [bucket][rank][bmax]; slots a launch did not use stay zero
+        ops.sumsq_partials(nv["table"], (len(self.buckets) if nv["overlap"] else 1) * self.world * nv["bmax"], out)
         return True
 
     def _join(self):
@@ -224,9 +227,17 @@ def nvls_setup(m, process_group=None):
         if p.grad is not None:
             p.grad = g[o:o + p.numel()].view(p.shape)
     m._bufs = {}   # recorded launch plans hold the old arena's pointers
-    # overlap (default): bucket by bucket beside the backward, `blocks` CTAs of `threads` threads per launch — one small CTA per SM
-    # fits next to a persistent GEMM CTA; ABCGPT_NVLS_OVERLAP=0: one exchange of the whole arena after the backward
-    return {"hdl": hdl, "thdl": thdl, "table": table, "overlap": os.environ.get("ABCGPT_NVLS_OVERLAP", "1") != "0",
+    # overlap (default): bucket by bucket beside the backward, `blocks` CTAs of `threads` threads per launch (one 128-thread CTA per SM
+    # fits next to a persistent GEMM CTA); the ranges released when the backward has ended go out in one full-size launch.
+    # ABCGPT_NVLS_OVERLAP=0: one exchange of the whole arena after the backward.
+    # Measured alternative (opt-in, ABCGPT_NVLS_DYNAMIC_TILES=1 with ABCGPT_NVLS_BLOCKS=16 ABCGPT_NVLS_THREADS=256): a co-resident CTA slows
+    # the GEMM CTA it shares an SM with by ~25 %, and a static tile schedule waits for the slowest SM (+13..48 % per GEMM in
+    # tools/coresidency_probe.py, +3..7 % with the ticket-based scheduler and 16 exchange CTAs) — in the 2-GPU step both forms measured
+    # the same (25.08 / 25.16 vs 25.14 ms), so the form validated on 8 GPUs stays the default.
+    overlap = os.environ.get("ABCGPT_NVLS_OVERLAP", "1") != "0"
+    if overlap and os.environ.get("ABCGPT_NVLS_DYNAMIC_TILES", "0") == "1":
+        ops.set_dynamic_tiles(True)
+    return {"hdl": hdl, "thdl": thdl, "table": table, "overlap": overlap,
             "blocks": int(os.environ.get("ABCGPT_NVLS_BLOCKS", "148")), "threads": int(os.environ.get("ABCGPT_NVLS_THREADS", "128"))}
 
 

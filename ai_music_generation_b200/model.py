@@ -555,6 +555,10 @@ class GPT(nn.Module):
         # overwrites a buffer, for the side-stream GEMM that read it (dxb, dh, dxb2, dqkv; the overwrite is most of a layer
         # later, so these waits are normally already satisfied).
         FORK, J0, J1, J2, J3 = 0, 1, 2, 3, 4
+        # experiment (ABCGPT_DDP_RELEASE=attn): a layer's gradient bucket is released a few kernels later, so that its exchange runs
+        # beside the next layer's attention backward instead of beside that layer's first GEMMs
+        release_beside_attn = sync is not None and os.environ.get("ABCGPT_DDP_RELEASE", "layer") == "attn"
+        held = None
         main_st = torch.cuda.current_stream()
 
         def wgrad(dy, xin, wname, jslot):
@@ -596,6 +600,9 @@ class GPT(nn.Module):
             wgrad(bufs.dxb2, bufs.att[li], "attn.c_proj", J2)
             ops.gemm(bufs.dxb2, lw["attn.c_proj.weight"][1], b_mn=True, epilogue=ops.EPI_BF16, out=bufs.datt)
             before_overwrite(J3)
+            if held is not None:   # the previous layer's bucket goes out beside this layer's attention backward (see below)
+                ops.record_callback(lambda li_=held: sync.layer_done(li_))
+                held = None
             ops.attn_bwd(bufs.qkv[li], bufs.att[li], bufs.datt, bufs.lse[li], bufs.delta, bufs.dqkv, B, T, H,
                          drop_p=p_drop, drop_key=keys[1 + 3 * li])
             wgrad(bufs.dqkv, bufs.ln1[li], "attn.c_attn", J3)
@@ -607,7 +614,10 @@ class GPT(nn.Module):
             dx, dx_other = dx_other, dx
             if sync is not None:
                 before_overwrite(J3)   # the layer's last wgrad (the side stream runs in order): its gradients are complete
-                ops.record_callback(lambda li=li: sync.layer_done(li))
+                if release_beside_attn and li > 0:
+                    held = li          # released right before the NEXT layer's attention backward
+                else:
+                    ops.record_callback(lambda li=li: sync.layer_done(li))
         before_overwrite(J3)           # join: everything the side stream was given has finished before the backward returns
         if mode == 1:
             ops.pos_bwd(dx, top["wpe"][2], T)
