@@ -50,6 +50,21 @@ def plan_buckets(layer_ranges, head_range, tail_range, bucket_elems, extra_range
     return buckets
 
 
+def merge_final_buckets(buckets):
+    """NVLS mode: the lowest layer group (trigger 0) joins the ranges released when the backward ends (trigger -1), and ranges that
+    are adjacent in the arena (head | group, patch embedding | 1-D tail) become one range — fewer exposed launches, each of which
+    sits between two device-side barriers.  The result still tiles exactly the same elements."""
+    last = [b for b in buckets if b[0] <= 0]
+    rest = [b for b in buckets if b[0] > 0]
+    merged = []
+    for _, lo, hi in sorted(last, key=lambda b: b[1]):
+        if merged and merged[-1][2] == lo:
+            merged[-1] = (-1, merged[-1][1], hi)
+        else:
+            merged.append((-1, lo, hi))
+    return rest + merged
+
+
 class GradSync:
     def __init__(self, grad_flat, layer_ranges, head_range, tail_range, process_group=None, bucket_mb=64.0,
                  extra_ranges=(), defer_final=False, nvls=None):
@@ -74,15 +89,7 @@ class GradSync:
             # every exchange costs a pair of device-side barriers, and the ones released at the END of the backward are exposed:
             # the lowest layer group joins the ranges around it (head | group | ... and patch embedding | 1-D tail are adjacent in
             # the arena), so the backward ends with one or two launches instead of four
-            last = [b for b in self.buckets if b[0] <= 0]
-            rest = [b for b in self.buckets if b[0] > 0]
-            merged = []
-            for _, lo, hi in sorted(last, key=lambda b: b[1]):
-                if merged and merged[-1][2] == lo:
-                    merged[-1] = (-1, merged[-1][1], hi)
-                else:
-                    merged.append((-1, lo, hi))
-            self.buckets = rest + merged
+            self.buckets = merge_final_buckets(self.buckets)
             self._by_trigger = {}
             for b in self.buckets:
                 self._by_trigger.setdefault(b[0], []).append(b)

@@ -101,6 +101,44 @@ def test_bucket_plan_extra_range_after_the_last_block():
     assert [(t, lo, hi) for t, lo, hi in buckets if t == -1] == [(-1, 0, 1000), (-1, 3100, 3600), (-1, 3600, 3700)]
 
 
+def test_nvls_final_ranges_are_merged_and_still_tile_the_arena():
+    """NVLS exchange (ddp.merge_final_buckets): the lowest layer group joins the ranges released at the end of the backward and
+    adjacent ranges become one launch; the set of exchanged elements must not change."""
+    from ai_music_generation_b200.ddp import merge_final_buckets, plan_buckets
+    layer_ranges = [(1000 + 700 * i, 1000 + 700 * (i + 1)) for i in range(12)]
+    for extra in ((), [(9400, 9500)]):
+        tail = (9500, 9560) if extra else (9400, 9460)
+        buckets = plan_buckets(layer_ranges, (0, 1000), tail, bucket_elems=700, extra_ranges=extra)
+        merged = merge_final_buckets(buckets)
+        covered = sorted((lo, hi) for _, lo, hi in merged)
+        assert covered[0][0] == 0 and covered[-1][1] == tail[1]
+        for (a, b), (c, d) in zip(covered, covered[1:]):
+            assert b == c
+        final = [(lo, hi) for t, lo, hi in merged if t == -1]
+        assert final == [(0, 1700), (9400, tail[1])]          # head | layer 0, and (patch embedding |) 1-D tail
+        assert [t for t, _, _ in merged if t > 0] == list(range(11, 0, -1))   # the other layers keep their release points
+        assert len(merged) == len(buckets) - (2 if extra else 1)
+
+
+def test_dropout_key_patches_of_a_recorded_plan():
+    """Launch plans recorded with dropout on are replayed with the next step's keys (ops.key_patches): every launch whose C
+    signature ends (..., dropout_p, dropout_key, stream) with p > 0 is a site; identical keys on two sites make the plan unusable."""
+    from ai_music_generation_b200 import ops
+    keys = [11, 22, 33, 44]
+    plan = [("embed_fwd", 1, None, (1, 2, 3, 0.2, 11, 99), ()), ("gemm", 1, None, (5, 6, 0.0, 0, 99), ()),
+            ("gemm", 1, None, (5, 6, 0.2, 33, 99), ()), ("layernorm_bwd", 1, None, (7, 0.2, 44, 99), ()), ("py", lambda: None),
+            ("sumsq", 2, None, (1, 2, 3), ())]
+    plan = [e if e[0] == "py" else e for e in plan]
+    patches = ops.key_patches(plan, keys)
+    assert patches == [(0, 0), (2, 2), (3, 3)]
+    new_keys = [101, 202, 303, 404]
+    for i, site in patches:
+        plan[i][3][-2] = new_keys[site]
+    assert plan[0][3][-2] == 101 and plan[2][3][-2] == 303 and plan[3][3][-2] == 404 and plan[1][3][-2] == 0
+    assert ops.key_patches([("gemm", 1, None, (0.2, 5, 99), ())], [5, 5]) is None        # two sites share a key
+    assert ops.key_patches([("gemm", 1, None, (0.2, 77, 99), ())], [5, 6]) is None       # a key that is not one of the step's
+
+
 def test_gradsync_two_ranks_gloo():
     script = os.path.join(ROOT, "tests", "_gloo_gradsync_worker.py")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
