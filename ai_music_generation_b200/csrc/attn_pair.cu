@@ -31,9 +31,6 @@ namespace abcgpt {
 namespace {
 
 constexpr int kSBuf = 3;          // S/dP score buffers in TMEM (as in csrc/attn.cu)
-#ifndef ABCGPT_EXP_SCORE_K
-#define ABCGPT_EXP_SCORE_K 4      // timing experiments only: fewer k-steps in the dQ kernel's score MMAs (wrong results)
-#endif
 constexpr int kRing = 6;          // streamed tiles in flight
 // Thread layout: warp 0 TMA, warp 1 score MMAs, warps 2..17 compute, warp 18 accumulating MMAs.
 // SIXTEEN compute warps (four per scheduler): the single-CTA kernels' two groups of four (two warps per scheduler, each
@@ -510,9 +507,9 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_con
           const uint64_t dK = dKV0 + static_cast<uint64_t>((gs % kRing) * (16384 >> 4)), dV = dK + (4096 >> 4);
           const uint32_t tS = tmem_base + (gs % kSBuf) * 128;
 #pragma unroll
-          for (int kk = 0; kk < ABCGPT_EXP_SCORE_K; ++kk) if (leader) ptx::umma_ss_2sm(tS, dQ0 + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ss_2sm(tS, dQ0 + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < ABCGPT_EXP_SCORE_K; ++kk) if (leader) ptx::umma_ss_2sm(tS + 64, dDO0 + 2 * kk, dV + 2 * kk, idesc_s, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) if (leader) ptx::umma_ss_2sm(tS + 64, dDO0 + 2 * kk, dV + 2 * kk, idesc_s, kk > 0);
           if (leader) ptx::umma_commit_2sm(&s_full[gs % kSBuf], 0x3);
         }
         if (leader) ptx::umma_commit_2sm(&qdo_empty[k & 1], 0x3);  // all score MMAs of the item done: Q / dO may be overwritten
