@@ -1175,6 +1175,26 @@ int gemm_bf16(const void* a, int a_mn, long long lda, const void* b, int b_mn, l
     // they need N > 128 to be worth a 256-wide tile.
     if (N > 128) {
       bn = 512;
+      // ... unless the problem is not 256-aligned: at the baby GPT's N = 384 a pair tile grid is a quarter padding (and 128 tiles on
+      // 74 pairs take two full rounds), where 128 x 128 single-CTA tiles waste nothing.  Cost in units of one pair-tile main loop;
+      // the single-CTA kernel pays ~15 % for its doubled operand traffic per FLOP.  MEASURED (tools/gemm_tile_sweep.py, 16384 tokens
+      // x 384): mlp.c_proj + residual 35.3 -> 31.3 us, dgrad attn.c_proj 14.4 -> 13.1, wgrad c_attn 23.3 -> 21.1, wgrad c_fc 27.3 ->
+      // 25.1 us; every 256-aligned shape (GPT-2-small, the hierarchical model) keeps the pair kernel.  ABCGPT_GEMM_AUTO128=0: off.
+      static const bool auto128 = [] {
+        const char* e = getenv("ABCGPT_GEMM_AUTO128");
+        return e == nullptr || e[0] != '0';
+      }();
+      const long long tp = static_cast<long long>((M + 255) / 256) * ((N + 255) / 256);
+      const long long t1 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
+      if (auto128 && epi == ABCGPT_EPI_F32_RED) {
+        // split-K balances the rounds whatever the tile: what differs is the padded output area (tokens = K here)
+        if (M >= 256 && K >= 4096 && 1.15 * static_cast<double>(t1) < 0.95 * 4.0 * static_cast<double>(tp)) bn = 128;
+      } else if (auto128 && M >= 4096) {
+        const long long P = sms / 2, r = tp % P;
+        const double rounds_pair = static_cast<double>(tp / P) + (r == 0 ? 0.0 : ((tp > P && 2 * r <= P) ? 0.5 : 1.0));
+        const double rounds_128 = static_cast<double>((t1 + sms - 1) / sms) * 0.5 * 1.15;
+        if (rounds_128 < 0.95 * rounds_pair) bn = 128;
+      }
     } else {
       bn = 128;
     }

@@ -400,6 +400,11 @@ def build_cases():
     cases["gemm2_half_gelu"] = lambda: case_gemm("gemm2_half_gelu", 2560, 2048, 128, False, False, E.EPI_GELU, 512, timing=False)
     cases["gemm2_half_dgelu"] = lambda: case_gemm("gemm2_half_dgelu", 2500, 2000, 128, False, True, E.EPI_DGELU, 512, timing=False)
     cases["gemm2_half_resid"] = lambda: case_gemm("gemm2_half_resid", 2500, 2000, 192, False, False, E.EPI_RESID, 512, timing=False)
+    # automatic tile choice (hint 0) at the baby GPT's shapes, where N = 384 sends the problem to 128 x 128 single-CTA tiles
+    cases["gemm_auto_cfg2_resid"] = lambda: case_gemm("gemm_auto_cfg2_resid", 16384, 384, 1536, False, False, E.EPI_RESID, 0, timing=False)
+    cases["gemm_auto_cfg2_dgrad"] = lambda: case_gemm("gemm_auto_cfg2_dgrad", 16384, 384, 384, False, True, E.EPI_BF16, 0, timing=False)
+    cases["gemm_auto_cfg2_dgelu"] = lambda: case_gemm("gemm_auto_cfg2_dgelu", 16384, 1536, 384, False, True, E.EPI_DGELU, 0, timing=False)
+    cases["gemm_auto_cfg2_wgrad"] = lambda: case_gemm("gemm_auto_cfg2_wgrad", 1152, 384, 16384, True, True, E.EPI_F32_RED, 0, timing=False)
     cases["gemm_nt_ragged"] = lambda: case_gemm("gemm_nt_ragged", 200, 96, 136, False, False, E.EPI_BF16, 128, timing=False)
     cases["gemm_nt_f32"] = lambda: case_gemm("gemm_nt_f32", 256, 256, 768, False, False, E.EPI_F32, 256, timing=False)
     cases["gemm_gelu"] = lambda: case_gemm("gemm_gelu", 512, 1536, 384, False, False, E.EPI_GELU, 0, timing=False)
